@@ -1,0 +1,206 @@
+"""ctypes bindings onto oracle/_ref/libsuzerain_ref.so.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The library is the
+reference's own hot-path C sources, compiled unmodified by oracle/Makefile,
+plus oracle/ref_shim/ref_glue.c.  Structures below mirror
+suzerain/rholut_imexop.h:66-133 and suzerain/bsplineop.h:125-180 field for
+field so that the reference functions can be called directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libsuzerain_ref.so")
+
+REF_NAMES = (
+    "ux uy uz u2 uxux uxuy uxuz uyuy uyuz uzuz nu nuux nuuy nuuz nuu2 "
+    "nuuxux nuuxuy nuuxuz nuuyuy nuuyuz nuuzuz ex_gradrho ey_gradrho "
+    "ez_gradrho e_divm e_deltarho").split()
+assert len(REF_NAMES) == 26
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class Scenario(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("Re", "Pr", "Ma", "alpha", "gamma")]
+
+
+class Ref(C.Structure):
+    _fields_ = [(n, c_double_p) for n in REF_NAMES]
+
+
+class RefLd(C.Structure):
+    _fields_ = [(n, C.c_int) for n in REF_NAMES]
+
+
+class Workspace(C.Structure):
+    _fields_ = [("method", C.c_int), ("k", C.c_int), ("n", C.c_int),
+                ("nderiv", C.c_int), ("kl", c_int_p), ("ku", c_int_p),
+                ("max_kl", C.c_int), ("max_ku", C.c_int), ("ld", C.c_int),
+                ("D_T", C.POINTER(c_double_p))]
+
+
+class Bc(C.Structure):
+    _fields_ = [("enforce_lower", C.c_int), ("enforce_upper", C.c_int),
+                ("E_factor", C.c_double * 2), ("vel_factor", (C.c_double * 3) * 2)]
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+        _lib.ref_set_blas_threads(1)
+    return _lib
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class Problem:
+    """Keeps numpy storage alive behind the reference's structs."""
+
+    def __init__(self, op, scenario: dict, refs: np.ndarray, bc: dict | None = None,
+                 nrbc=None):
+        """op: oracle.bspline.BsplineOp; refs: (26, n) float64 in REF_NAMES order.
+        bc: dict(enforce_lower, enforce_upper, E_factor[2], vel_factor[2][3]).
+        nrbc: None or (a, b, c) each 5x5 column-major float64."""
+        self.op = op
+        self.n = op.n
+        self.scen = Scenario(**{k: float(scenario[k]) for k in ("Re", "Pr", "Ma", "alpha", "gamma")})
+        self.refs = np.ascontiguousarray(refs, dtype=np.float64)
+        assert self.refs.shape == (26, op.n)
+        self.ref = Ref()
+        self.refld = RefLd()
+        for q, name in enumerate(REF_NAMES):
+            setattr(self.ref, name, _p(self.refs[q]))
+            setattr(self.refld, name, 1)
+        # workspace: only D_T[0..2] are read by the hot path (rholut_imexop.c:77)
+        nd = op.nderiv
+        self._storage = np.ascontiguousarray(op.storage)
+        self._kl = np.ascontiguousarray(op.kl, dtype=np.int32)
+        self._ku = np.ascontiguousarray(op.ku, dtype=np.int32)
+        self._DT = (c_double_p * (nd + 1))()
+        base = self._storage.ctypes.data
+        for d in range(nd + 1):
+            addr = base + 8 * (d * op.n * op.ld + op.D_T_offset(d))
+            self._DT[d] = C.cast(addr, c_double_p)
+        self.w = Workspace(0, op.k, op.n, nd, _p(self._kl, C.c_int), _p(self._ku, C.c_int),
+                           op.max_kl, op.max_ku, op.ld, self._DT)
+        self.bc = None
+        if bc is not None:
+            self.bc = Bc()
+            self.bc.enforce_lower = int(bc.get("enforce_lower", 1))
+            self.bc.enforce_upper = int(bc.get("enforce_upper", 1))
+            for i in range(2):
+                self.bc.E_factor[i] = float(bc["E_factor"][i])
+                for j in range(3):
+                    self.bc.vel_factor[i][j] = float(bc["vel_factor"][i][j])
+        self.nrbc = None
+        if nrbc is not None:
+            self.nrbc = tuple(None if m is None else np.ascontiguousarray(
+                np.asarray(m, dtype=np.float64).reshape(-1)) for m in nrbc)
+        self.S = 5
+        self.N = 5 * op.n
+        self.KL = 5 * (op.max_kl + 1) - 1
+        self.KU = 5 * (op.max_ku + 1) - 1
+        self.LD = self.KL + 1 + self.KU
+
+    def _abc(self):
+        if self.nrbc is None:
+            return None, None, None
+        return tuple(_p(m) for m in self.nrbc)
+
+    def assemble(self, phi: complex, km: float, kn: float, packf=False, with_bc=True):
+        rows = self.LD + (self.KL if packf else 0)
+        out = np.full((self.N, rows), np.nan + 1j * np.nan, dtype=np.complex128)
+        phi2 = (C.c_double * 2)(phi.real, phi.imag)
+        a, b, c = self._abc()
+        rc = lib().ref_assemble(phi2, C.c_double(km), C.c_double(kn),
+                                C.byref(self.scen), C.byref(self.ref), C.byref(self.refld),
+                                C.byref(self.w),
+                                C.byref(self.bc) if (with_bc and self.bc is not None) else None,
+                                a, b, c, int(packf), out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return out                      # [column j, band row]
+
+    def invert(self, solver: str, phi: complex, km, kn, state, extra=None, nthreads=1,
+               want_ipiv=False, want_iters=False):
+        """state: (npencil, 5*n) complex128, solved in place (copy returned)."""
+        km = np.ascontiguousarray(km, dtype=np.float64)
+        kn = np.ascontiguousarray(kn, dtype=np.float64)
+        x = np.array(state, dtype=np.complex128, order="C", copy=True)
+        npencil = x.shape[0]
+        assert x.shape == (npencil, self.N) and km.shape == (npencil,) == kn.shape
+        nextra = 0
+        ex = None
+        if extra is not None:
+            ex = np.array(extra, dtype=np.complex128, order="C", copy=True)
+            nextra = ex.shape[1]
+            assert ex.shape == (npencil, nextra, self.N)
+        ipiv = np.zeros((npencil, self.N), dtype=np.int32) if want_ipiv else None
+        iters = np.zeros(npencil, dtype=np.int32) if want_iters else None
+        bad = C.c_int(-1)
+        phi2 = (C.c_double * 2)(phi.real, phi.imag)
+        a, b, c = self._abc()
+        assert self.bc is not None
+        info = lib().ref_invert_batch(
+            {"zgbsv": 0, "zcgbsvx": 1}[solver], phi2,
+            C.byref(self.scen), C.byref(self.ref), C.byref(self.refld), C.byref(self.w),
+            C.byref(self.bc), a, b, c, npencil, _p(km), _p(kn),
+            x.ctypes.data_as(C.c_void_p), nextra,
+            ex.ctypes.data_as(C.c_void_p) if ex is not None else None,
+            _p(ipiv, C.c_int), _p(iters, C.c_int), int(nthreads), C.byref(bad))
+        res = {"x": x, "info": info, "first_bad": bad.value}
+        if ex is not None:
+            res["extra"] = ex
+        if want_ipiv:
+            res["ipiv"] = ipiv
+        if want_iters:
+            res["iters"] = iters
+        return res
+
+    def accumulate(self, phi: complex, km, kn, x, beta: complex = 0.0, y=None, nthreads=1):
+        km = np.ascontiguousarray(km, dtype=np.float64)
+        kn = np.ascontiguousarray(kn, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        npencil = x.shape[0]
+        out = (np.zeros_like(x) if y is None
+               else np.array(y, dtype=np.complex128, order="C", copy=True))
+        phi2 = (C.c_double * 2)(complex(phi).real, complex(phi).imag)
+        beta2 = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+        a, b, c = self._abc()
+        lib().ref_accumulate_batch(phi2, C.byref(self.scen), C.byref(self.ref),
+                                   C.byref(self.refld), C.byref(self.w), a, b, c,
+                                   npencil, _p(km), _p(kn),
+                                   x.ctypes.data_as(C.c_void_p), beta2,
+                                   out.ctypes.data_as(C.c_void_p), int(nthreads))
+        return out
+
+
+def zgbsv_T(N, KL, KU, LU, B):
+    """In-place zgbtrf + zgbtrs('T') on LAPACK band storage.
+    LU: (N, 2KL+KU+1) complex128 C-contiguous == column-major (2KL+KU+1) x N.
+    B: (nrhs, N).  Returns (LU, ipiv, X, info)."""
+    LU = np.array(LU, dtype=np.complex128, order="C", copy=True)
+    B = np.array(B, dtype=np.complex128, order="C", copy=True).reshape(-1, N)
+    ipiv = np.zeros(N, dtype=np.int32)
+    info = lib().ref_zgbsv_T(N, KL, KU, LU.ctypes.data_as(C.c_void_p), 2 * KL + KU + 1,
+                             _p(ipiv, C.c_int), B.ctypes.data_as(C.c_void_p), B.shape[0])
+    return LU, ipiv, B, info
+
+
+def q(S, n, i):
+    return lib().suzerain_bsmbsm_q(S, n, i) if hasattr(lib(), "suzerain_bsmbsm_q") else (i % S) * n + i // S
