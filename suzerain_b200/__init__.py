@@ -1,0 +1,12 @@
+"""suzerain_b200 -- B200-native implicit wall-normal operator path of Suzerain.
+
+The product is ``libsuzerain_b200.so`` (hand-written sm_100a FP64 CUDA behind the
+C ABI of ``include/suzerain_b200.h``); this package is the thin host-side mirror
+of the reference's operator interface used by tests and ``bench.py``.
+"""
+from . import lib  # noqa: F401
+from .api import (BsplineOp, ImexOp, OperatorHybridIsothermal, SolverSpec,  # noqa: F401
+                  htstretch_breakpoints, wavegrid, wavenumbers)
+
+__all__ = ["lib", "BsplineOp", "ImexOp", "OperatorHybridIsothermal", "SolverSpec",
+           "htstretch_breakpoints", "wavegrid", "wavenumbers"]

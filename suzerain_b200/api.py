@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's operator interface over the C ABI.
+
+Names follow the reference: ``BsplineOp`` ~ ``suzerain::bsplineop``
+(suzerain/bspline.hpp:348-590), ``ImexOp`` ~ the per-pencil
+``suzerain_rholut_imexop_*`` family (suzerain/rholut_imexop.h) bound to a
+scenario / reference profiles / wall data, and ``OperatorHybridIsothermal`` ~
+``suzerain::perfect::operator_hybrid_isothermal``
+(apps/perfect/operator_hybrid_isothermal.hpp:101-140) with its three
+``*_mass_plus_scaled_operator`` methods.
+
+Device arrays are ``torch`` CUDA tensors (torch is only the allocator / stream
+provider here); every computation is a call into libsuzerain_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+
+from . import lib as _L
+
+
+def _d2(z):
+    z = complex(z)
+    return (C.c_double * 2)(z.real, z.imag)
+
+
+def _ptr(t):
+    """Raw device/host pointer of a torch tensor or numpy array (or None)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def _stream_handle(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if hasattr(stream, "cuda_stream"):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+class BsplineOp:
+    """B-spline Greville-collocation operators D^(0..nderiv) (host)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        L = _L.load()
+        h = C.c_void_p(handle)
+        self.k = L.szb_bsplineop_k(h)
+        self.n = L.szb_bsplineop_n(h)
+        self.nderiv = L.szb_bsplineop_nderiv(h)
+        self.kl = np.array([L.szb_bsplineop_kl(h, d) for d in range(self.nderiv + 1)], dtype=np.int32)
+        self.ku = np.array([L.szb_bsplineop_ku(h, d) for d in range(self.nderiv + 1)], dtype=np.int32)
+        self.max_kl = L.szb_bsplineop_max_kl(h)
+        self.max_ku = L.szb_bsplineop_max_ku(h)
+        self.ld = L.szb_bsplineop_ld(h)
+
+    @classmethod
+    def from_breakpoints(cls, k, breakpoints, nderiv=None):
+        L = _L.load()
+        b = np.ascontiguousarray(breakpoints, dtype=np.float64)
+        if nderiv is None:
+            nderiv = max(k - 2, 0)           # suzerain/support/support.cpp:308
+        h = C.c_void_p()
+        _L.check("szb_bsplineop_alloc",
+                 L.szb_bsplineop_alloc(k, len(b), b.ctypes.data_as(_L.c_double_p), nderiv, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_storage(cls, k, n, nderiv, kl, ku, storage):
+        L = _L.load()
+        kl = np.ascontiguousarray(kl, dtype=np.int32)
+        ku = np.ascontiguousarray(ku, dtype=np.int32)
+        st = np.ascontiguousarray(storage, dtype=np.float64)
+        h = C.c_void_p()
+        _L.check("szb_bsplineop_from_storage",
+                 L.szb_bsplineop_from_storage(k, n, nderiv, kl.ctypes.data_as(_L.c_int_p),
+                                              ku.ctypes.data_as(_L.c_int_p),
+                                              st.ctypes.data_as(_L.c_double_p), C.byref(h)))
+        return cls(h.value)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _L.load().szb_bsplineop_free(C.c_void_p(self._h))
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return C.c_void_p(self._h)
+
+    @property
+    def storage(self):
+        """(nderiv+1, n, ld) copy of the operator block in the reference's layout:
+        storage[d, i, max_ku + j - i] = D^(d)[i, j]."""
+        L = _L.load()
+        out = np.empty((self.nderiv + 1, self.n, self.ld))
+        for d in range(self.nderiv + 1):
+            p = L.szb_bsplineop_D_T(self.handle, d)
+            addr = C.addressof(p.contents) - 8 * int(self.max_ku - self.ku[d])
+            buf = (C.c_double * (self.n * self.ld)).from_address(addr)
+            out[d] = np.frombuffer(buf, dtype=np.float64).reshape(self.n, self.ld)
+        return out
+
+    def D_T_offset(self, d):
+        return int(self.max_ku - self.ku[d])
+
+    def greville(self):
+        xi = np.empty(self.n)
+        _L.check("szb_bsplineop_greville",
+                 _L.load().szb_bsplineop_greville(self.handle, xi.ctypes.data_as(_L.c_double_p)))
+        return xi
+
+    def dense(self, d):
+        st = self.storage[d]
+        out = np.zeros((self.n, self.n))
+        for i in range(self.n):
+            for j in range(max(0, i - self.max_ku), min(self.n, i + self.max_kl + 1)):
+                out[i, j] = st[i, self.max_ku + j - i]
+        return out
+
+
+def htstretch_breakpoints(ndof, k, left, right, htdelta):
+    """suzerain/support/support.cpp:288-300."""
+    L = _L.load()
+    x = np.linspace(0.0, 1.0, ndof - k + 2)
+    if htdelta >= 0:
+        b = np.array([L.szb_htstretch2(+htdelta, 1.0, v) for v in x])
+    else:
+        b = np.array([L.szb_htstretch1(-htdelta, 1.0, v) for v in x])
+    return (right - left) * b + left
+
+
+@dataclasses.dataclass
+class SolverSpec:
+    """specification_zgbsv (suzerain/specification_zgbsv.cpp:46-124)."""
+    method: str = "zcgbsvx"
+    aiter: int = 1
+    diter: int = 5
+    tolsc: float = 0.0
+
+    @classmethod
+    def parse(cls, text: str):
+        """Accepts the reference grammar subset: zgbsv | zcgbsvx[,aiter=i,diter=i,tolsc=d]."""
+        parts = [p.strip() for p in text.split(",") if p.strip()]
+        if not parts or parts[0] not in ("zgbsv", "zcgbsvx"):
+            raise ValueError(f"unsupported solver specification {text!r}")
+        spec = cls(method=parts[0])
+        for kv in parts[1:]:
+            key, _, val = kv.partition("=")
+            key = key.strip()
+            if spec.method != "zcgbsvx" or key not in ("aiter", "diter", "tolsc", "reuse", "siter"):
+                raise ValueError(f"unknown option {kv!r} in {text!r}")
+            if key == "tolsc":
+                spec.tolsc = float(val)
+            elif key == "aiter":
+                spec.aiter = int(val)
+            elif key == "diter":
+                spec.diter = int(val)
+            elif key == "reuse" and val.strip().lower() not in ("0", "false", "no"):
+                raise ValueError("reuse=true is not supported")
+            elif key == "siter" and int(val) >= 0:
+                raise ValueError("single-precision refinement (siter>=0) is not supported")
+        return spec
+
+    def c(self):
+        return _L.ZgbsvSpec({"zgbsv": 0, "zcgbsvx": 1}[self.method], self.aiter, self.diter, self.tolsc)
+
+
+class ImexOp:
+    """Device-resident (M + phi L) for one scenario / set of reference profiles."""
+
+    def __init__(self, bop: BsplineOp):
+        self.bop = bop
+        h = C.c_void_p()
+        _L.check("szb_imexop_create", _L.load().szb_imexop_create(bop.handle, C.byref(h)))
+        self._h = h.value
+        A = _L.load().szb_imexop_bsmbsm(self.handle)
+        self.S, self.n, self.N, self.KL, self.KU, self.LD = A.S, A.n, A.N, A.KL, A.KU, A.LD
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if self._h:
+                _L.load().szb_imexop_destroy(C.c_void_p(self._h))
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return C.c_void_p(self._h)
+
+    def set_scenario(self, Re, Pr, Ma, alpha, gamma):
+        s = _L.Scenario(Re, Pr, Ma, alpha, gamma)
+        _L.check("szb_imexop_set_scenario", _L.load().szb_imexop_set_scenario(self.handle, C.byref(s)))
+        return self
+
+    def set_refs(self, refs, stride=None):
+        """refs: (26, n) array in lib.REF_NAMES order, or a (n, 42)-style array
+        plus explicit row map via ``stride`` is not needed here: rows are dense."""
+        refs = np.ascontiguousarray(refs, dtype=np.float64)
+        assert refs.shape == (26, self.n)
+        r, ld = _L.Ref(), _L.RefLd()
+        for q, name in enumerate(_L.REF_NAMES):
+            setattr(r, name, refs[q].ctypes.data_as(_L.c_double_p))
+            setattr(ld, name, 1)
+        _L.check("szb_imexop_set_refs", _L.load().szb_imexop_set_refs(self.handle, C.byref(r), C.byref(ld)))
+        return self
+
+    def set_isothermal(self, enforce_lower=True, enforce_upper=True, lower=(1.0, 0.0, 0.0, 0.0),
+                       upper=(1.0, 0.0, 0.0, 0.0)):
+        iso = _L.Isothermal(int(enforce_lower), int(enforce_upper), *map(float, lower), *map(float, upper))
+        _L.check("szb_imexop_set_isothermal",
+                 _L.load().szb_imexop_set_isothermal(self.handle, C.byref(iso)))
+        return self
+
+    def set_nrbc(self, a=None, b=None, c=None):
+        arrs = [None if m is None else np.ascontiguousarray(np.asarray(m, dtype=np.float64).reshape(-1))
+                for m in (a, b, c)]
+        ptrs = [None if m is None else m.ctypes.data_as(_L.c_double_p) for m in arrs]
+        _L.check("szb_imexop_set_nrbc", _L.load().szb_imexop_set_nrbc(self.handle, *ptrs))
+        return self
+
+    # ---- batched, device tensors ------------------------------------------------
+    def accumulate_batch(self, phi, km, kn, x, beta, y, index=None, x_strides=None,
+                         y_strides=None, stream=None):
+        """y <- (M + phi L) x + beta y on device tensors.
+        x, y: complex128 CUDA tensors; default layout (npencil, 5, n) contiguous,
+        i.e. field stride n and pencil stride 5n (interleaved-state pencils)."""
+        n = self.n
+        xs = x_strides or (n, 5 * n)
+        ys = y_strides or (n, 5 * n)
+        rc = _L.load().szb_imexop_accumulate_batch(
+            self.handle, _d2(phi), int(km.numel()), _ptr(km), _ptr(kn), _ptr(index),
+            _ptr(x), xs[0], xs[1], _d2(beta), _ptr(y), ys[0], ys[1], _stream_handle(stream))
+        _L.check("szb_imexop_accumulate_batch", rc)
+        return y
+
+    def pack_batch(self, phi, km, kn, out, packf=False, with_bc=False, stream=None):
+        rc = _L.load().szb_imexop_pack_batch(self.handle, _d2(phi), int(km.numel()), _ptr(km),
+                                             _ptr(kn), int(packf), int(with_bc), _ptr(out),
+                                             _stream_handle(stream))
+        _L.check("szb_imexop_pack_batch", rc)
+        return out
+
+    def invert_batch(self, spec: SolverSpec, phi, km, kn, state, index=None, strides=None,
+                     extra=None, ipiv=None, info=None, iters=None, stream=None):
+        n = self.n
+        st = strides or (n, 5 * n)
+        cs = spec.c()
+        nextra = 0 if extra is None else int(extra.shape[1])
+        rc = _L.load().szb_imexop_invert_batch(
+            self.handle, C.byref(cs), _d2(phi), int(km.numel()), _ptr(km), _ptr(kn), _ptr(index),
+            _ptr(state), st[0], st[1], nextra, _ptr(extra), _ptr(ipiv), _ptr(info), _ptr(iters),
+            _stream_handle(stream))
+        _L.check("szb_imexop_invert_batch", rc)
+        return state
+
+    def workspace_bytes(self):
+        return int(_L.load().szb_imexop_workspace_bytes(self.handle))
+
+
+def wavegrid(Nx, Nz, Lx, Lz, dealias=1.5, xrange=None, zrange=None):
+    """specification_grid / pencil_grid extents for one rank owning
+    [xrange) x [zrange) of wave space (defaults: everything).  dN = dealias*N,
+    wave-space x extent is dNx/2+1 (real-to-complex transform)."""
+    dNx, dNz = int(Nx * dealias), int(Nz * dealias)
+    xb, xe = xrange if xrange is not None else (0, dNx // 2 + 1)
+    zb, ze = zrange if zrange is not None else (0, dNz)
+    return _L.WaveGrid(Nx, dNx, xb, xe, Nz, dNz, zb, ze, float(Lx), float(Lz))
+
+
+def wavenumbers(g):
+    L = _L.load()
+    npen = L.szb_wavegrid_npencils(C.byref(g))
+    km, kn = np.empty(npen), np.empty(npen)
+    act = np.empty(npen, dtype=np.int32)
+    L.szb_wavegrid_wavenumbers(C.byref(g), km.ctypes.data_as(_L.c_double_p),
+                               kn.ctypes.data_as(_L.c_double_p), act.ctypes.data_as(_L.c_int_p))
+    return km, kn, act.astype(bool)
+
+
+class OperatorHybridIsothermal:
+    """The three virtuals of operator_hybrid_isothermal on HOST state arrays
+    (numpy, optionally pinned); copies to the device and back inside each call
+    (apps/perfect/operator_hybrid_isothermal.cpp:103,243,528)."""
+
+    def __init__(self, imexop: ImexOp, grid, spec: SolverSpec | None = None):
+        self.op = imexop
+        self.grid = grid
+        self.spec = spec or SolverSpec()
+
+    def apply_mass_plus_scaled_operator(self, phi, state):
+        rc = _L.load().szb_operator_apply_mass_plus_scaled_operator(
+            self.op.handle, C.byref(self.grid), _d2(phi), _ptr(state))
+        _L.check("szb_operator_apply_mass_plus_scaled_operator", rc)
+        return state
+
+    def accumulate_mass_plus_scaled_operator(self, phi, input, beta, output, out_field_stride):
+        rc = _L.load().szb_operator_accumulate_mass_plus_scaled_operator(
+            self.op.handle, C.byref(self.grid), _d2(phi), _ptr(input), _d2(beta), _ptr(output),
+            int(out_field_stride))
+        _L.check("szb_operator_accumulate_mass_plus_scaled_operator", rc)
+        return output
+
+    def invert_mass_plus_scaled_operator(self, phi, state, ic0=None):
+        bad = C.c_int(-1)
+        cs = self.spec.c()
+        nc = 0 if ic0 is None else int(ic0.shape[0])
+        rc = _L.load().szb_operator_invert_mass_plus_scaled_operator(
+            self.op.handle, C.byref(cs), C.byref(self.grid), _d2(phi), _ptr(state), nc, _ptr(ic0),
+            C.byref(bad))
+        if rc > 0:
+            # bsmbsm_solver.cpp:123-141: decode the singular row
+            N, n = self.op.N, self.op.n
+            row = rc - 1
+            q = (row % 5) * n + row // 5
+            raise _L.SzbError(
+                f"invert: pencil {bad.value}: singularity in PAP^T row {row} corresponding to "
+                f"A row {q} for state scalar {q // n}", rc)
+        _L.check("szb_operator_invert_mass_plus_scaled_operator", rc)
+        return state

@@ -1,0 +1,442 @@
+// imexop.cu -- device-resident (M + phi L) operator context and the batched
+// accumulate / apply and assembly kernels.
+//
+// Replaces suzerain_rholut_imexop_accumulate (suzerain/rholut_imexop.c:43-547),
+// suzerain_rholut_imexop_pack{c,f} (suzerain/rholut_imexop.def:41-597),
+// suzerain_bsmbsm_z{,d}pack (suzerain/bsmbsm_pack.def:37-123) and
+// IsothermalPATPTEnforcer::op (apps/perfect/operator_hybrid_isothermal.cpp:
+// 470-510) with kernels that work on every local (kx,kz) pencil in one launch.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <atomic>
+
+#include "szb_internal.hpp"
+#include "cplx.cuh"
+#include "kernels.cuh"
+
+namespace szb {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(unsigned n) { g_launches += n; }
+
+void report_cuda(cudaError_t e, const char *what, const char *file, int line)
+{
+    std::fprintf(stderr, "suzerain_b200: CUDA error %d (%s) at %s:%d: %s\n",
+                 (int) e, cudaGetErrorString(e), file, line, what);
+}
+
+// ---------------------------------------------------------------------------
+// Term table construction (host): fold the scenario into per-term constants.
+// ---------------------------------------------------------------------------
+static void build_terms(const szb_rholut_imexop_scenario &s, TermTable &tt)
+{
+    // Shorthands as in rholut_imexop.c:85-97
+    const double g        = s.gamma;
+    const double gm1      = s.gamma - 1;
+    const double gm3      = s.gamma - 3;
+    const double ap43     = s.alpha + 4.0 / 3.0;
+    const double ap13     = s.alpha + 1.0 / 3.0;
+    const double Ma2      = s.Ma * s.Ma;
+    const double invRe    = 1 / s.Re;
+    const double invMa2   = 1 / Ma2;
+    const double ginvPr   = s.gamma / s.Pr;
+    const double ginvRePr = s.gamma / (s.Re * s.Pr);
+    (void) g; (void) gm3; (void) invMa2;
+
+    std::memset(&tt, 0, sizeof(tt));
+    int t = 0, last_blk = -1;
+    for (int b = 0; b <= NBLOCK; ++b) tt.blk_begin[b] = 0;
+    auto add = [&](int row, int col, int op, int ref, int wave, double sc) {
+        const int blk = (row * NFIELD + col) * NOPER + op;
+        // blocks arrive in increasing order; close all blocks up to this one
+        for (int b = last_blk + 1; b <= blk; ++b) tt.blk_begin[b] = (uint8_t) t;
+        last_blk = blk;
+        tt.sc[t] = sc; tt.ref[t] = (uint8_t) ref; tt.wave[t] = (uint8_t) wave;
+        ++t;
+    };
+#define SZB_TERM(row, col, op, ref, wave, scen) \
+    add(szb::row, szb::col, szb::op, refid::ref, wavid::wave, (scen));
+#include "rholut_terms.def"
+#undef SZB_TERM
+    for (int b = last_blk + 1; b <= NBLOCK; ++b) tt.blk_begin[b] = (uint8_t) t;
+    tt.nterms = t;
+}
+
+// ---------------------------------------------------------------------------
+// accumulate: out <- (M + phi L) in + beta out, one CTA per pencil.
+//
+// Layout in shared memory: the five input pencils (5*n complex) and the
+// per-term coefficients alpha_t = phi * sc_t * wave_t(km, kn).
+// Each thread owns collocation points y = tid, tid + blockDim, ...:
+//   P[d][j] = sum_r D^(d)[y, y - ku + r] * in_j[y - ku + r]     (15 banded dots)
+//   out_i   = beta out_i + sum_{blocks (i,j,d)} (sum_t alpha_t ref_t[y]) P[d][j]
+//             + P[M][i]                                   (mass added last)
+// The block structure is unrolled at compile time from rholut_terms.def so
+// P and the accumulators stay in registers.
+// ---------------------------------------------------------------------------
+struct AccumulateArgs {
+    const double *D;        // [3][ld][n]  (r-major: D[(d*ld + r)*n + y])
+    const double *refs;     // [27][n]
+    const TermTable *terms;
+    int n, kl, ku, ld;
+    cplx phi, beta;
+    const double *km, *kn; const int *index;
+    const cplx *in;  size_t in_fs,  in_ps;
+    cplx       *out; size_t out_fs, out_ps;
+    int nrbc;               // bit0 a, bit1 b, bit2 c
+    double a[25], b[25], c[25];
+};
+
+__global__ void __launch_bounds__(128)
+accumulate_kernel(const AccumulateArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *s_in    = reinterpret_cast<cplx *>(smem_raw);            // [5][n]
+    cplx *s_alpha = s_in + 5 * A.n;                                // [nterms]
+
+    const int p = blockIdx.x;
+    const int n = A.n;
+    const double km = A.km[p], kn = A.kn[p];
+    const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
+    const cplx *in = A.in + slot * A.in_ps;
+    cplx *out = A.out + slot * A.out_ps;
+
+    for (int e = threadIdx.x; e < 5 * n; e += blockDim.x) {
+        const int f = e / n, y = e - f * n;
+        s_in[e] = in[(size_t) f * A.in_fs + y];
+    }
+    const int nterms = A.terms->nterms;
+    for (int t = threadIdx.x; t < nterms; t += blockDim.x) {
+        const cplx w = wave_factor(A.terms->wave[t], km, kn);
+        s_alpha[t] = A.phi * (w * A.terms->sc[t]);
+    }
+    __syncthreads();
+
+    const bool beta_zero = is_zero(A.beta);
+    const bool nrbc = A.nrbc != 0;
+
+    for (int y = threadIdx.x; y < n; y += blockDim.x) {
+        // --- 15 banded products ---
+        cplx P[3][5];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) P[d][j] = cplx(0.0, 0.0);
+        const int r0 = max(0, A.ku - y), r1 = min(A.ld, n - y + A.ku);
+        for (int r = r0; r < r1; ++r) {
+            const int x = y - A.ku + r;
+            const double m0 = A.D[(size_t) (0 * A.ld + r) * n + y];
+            const double m1 = A.D[(size_t) (1 * A.ld + r) * n + y];
+            const double m2 = A.D[(size_t) (2 * A.ld + r) * n + y];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const cplx v = s_in[j * n + x];
+                addmul(P[0][j], v, m0);
+                addmul(P[1][j], v, m1);
+                addmul(P[2][j], v, m2);
+            }
+        }
+
+        // --- reference profiles at y ---
+        double rf[REF_ONE + 1];
+#pragma unroll
+        for (int q = 0; q <= REF_ONE; ++q) rf[q] = A.refs[(size_t) q * n + y];
+
+        const bool top = nrbc && (y == n - 1);
+        cplx acc[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            acc[i] = (beta_zero || top) ? cplx(0.0, 0.0)
+                                        : A.beta * out[(size_t) i * A.out_fs + y];
+        }
+
+        // --- block contributions, statically unrolled ---
+        {
+            int t = 0, cur = -1, crow = 0, ccol = 0, cop = 0;
+            cplx c(0.0, 0.0);
+#define SZB_FLUSH() do { if (cur >= 0) acc[crow] += c * P[cop][ccol]; } while (0)
+#define SZB_TERM(row, col, op, ref, wave, scen)                              \
+            if ((szb::row * 5 + szb::col) * 3 + szb::op != cur) {            \
+                SZB_FLUSH();                                                 \
+                cur = (szb::row * 5 + szb::col) * 3 + szb::op;               \
+                crow = szb::row; ccol = szb::col; cop = szb::op;             \
+                c = cplx(0.0, 0.0);                                          \
+            }                                                                \
+            c += s_alpha[t] * rf[refid::ref]; ++t;
+#include "rholut_terms.def"
+#undef SZB_TERM
+            SZB_FLUSH();
+#undef SZB_FLUSH
+        }
+
+        cplx phiL[5];
+        if (top) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                phiL[i] = acc[i];
+                acc[i] = beta_zero ? acc[i]
+                                   : A.beta * out[(size_t) i * A.out_fs + y] + acc[i];
+            }
+        }
+        // mass last
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc[i] += P[0][i];
+
+        if (top) {
+            // NRBC upper-boundary correction (rholut_imexop.c:510-545)
+            cplx tt[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) tt[i] = cplx(0.0, 0.0);
+            const cplx ikmphi = cplx(0.0, km) * A.phi;
+            const cplx iknphi = cplx(0.0, kn) * A.phi;
+            if (A.nrbc & 1) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    cplx s(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.a[i + 5 * j];
+                    tt[i] -= ikmphi * s;
+                }
+            }
+            if (A.nrbc & 2) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    cplx s(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.b[i + 5 * j];
+                    tt[i] -= iknphi * s;
+                }
+            }
+            if (A.nrbc & 4) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    cplx s(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) s += phiL[j] * A.c[i + 5 * j];
+                    tt[i] -= s;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) acc[i] += tt[i];
+        }
+
+#pragma unroll
+        for (int i = 0; i < 5; ++i) out[(size_t) i * A.out_fs + y] = acc[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pack: assemble P (M + phi L)^T P^T into LAPACK band storage, one CTA per
+// pencil (see pack_pencil in kernels.cuh).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_kernel(const PackArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *s_alpha = reinterpret_cast<cplx *>(smem_raw);
+    __shared__ cplx s_x[75];
+    const int p = blockIdx.x;
+    cplx *M = A.out + (size_t) p * A.N * A.rows + A.rowoff;
+    pack_pencil(A, A.rows, A.km[p], A.kn[p], s_alpha, s_x, M);
+}
+
+}  // namespace szb
+
+using namespace szb;
+
+// ---------------------------------------------------------------------------
+// C ABI: context management
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *szb_version(void) { return "suzerain_b200 0.1 (sm_100a, FP64)"; }
+unsigned long long szb_launch_count(void) { return szb::g_launches.load(); }
+
+int szb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+szb_zgbsv_spec szb_zgbsv_spec_default(void)
+{
+    szb_zgbsv_spec s;
+    s.method = SZB_SOLVER_ZCGBSVX; s.aiter = 1; s.diter = 5; s.tolsc = 0.0;
+    return s;
+}
+
+int szb_imexop_create(const szb_bsplineop *w, szb_imexop **out)
+{
+    if (!w) return -1;
+    if (!out) return -2;
+    if (w->nderiv < 2) return -1;                   // rholut_imexop.c:77
+    szb_imexop *op = new (std::nothrow) szb_imexop();
+    if (!op) return -2;
+    std::memset(&op->scen, 0, sizeof(op->scen));
+    op->n = w->n; op->k = w->k; op->kl = w->max_kl; op->ku = w->max_ku; op->ld = w->ld;
+    op->A = szb_bsmbsm_construct(5, w->n, w->max_kl, w->max_ku);
+    op->d_D = nullptr; op->d_refs = nullptr; op->d_terms = nullptr;
+    op->d_work = nullptr; op->work_bytes = 0; op->work_slots = 0;
+    op->have_a = op->have_b = op->have_c = false;
+    std::memset(&op->iso, 0, sizeof(op->iso));
+    op->iso.enforce_lower = 1; op->iso.enforce_upper = 1;
+    for (int i = 0; i < 2; ++i) { op->E_factor[i] = 0; for (int j = 0; j < 3; ++j) op->vel_factor[i][j] = 0; }
+
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { delete op; report_cuda(e, "cudaGetDevice", __FILE__, __LINE__); return SZB_ECUDA_BASE - (int) e; }
+    cudaDeviceGetAttribute(&op->sm_count, cudaDevAttrMultiProcessorCount, dev);
+
+    // Operators in r-major order with the common (max) bandwidth view:
+    // h[(d*ld + r)*n + i] = D^(d)[i, i - ku + r] = (D_T[d] - (max_ku - ku[d]))[i*ld + r]
+    const int n = op->n, ld = op->ld;
+    std::vector<double> h((size_t) 3 * ld * n, 0.0);
+    for (int d = 0; d < 3; ++d) {
+        const double *blk = w->storage.data() + (size_t) d * ld * n;
+        for (int i = 0; i < n; ++i)
+            for (int r = 0; r < ld; ++r)
+                h[((size_t) d * ld + r) * n + i] = blk[(size_t) i * ld + r];
+    }
+    std::vector<double> ones((size_t) (SZB_NREF + 1) * n, 0.0);
+    for (int i = 0; i < n; ++i) ones[(size_t) SZB_NREF * n + i] = 1.0;
+    if ((e = cudaMalloc(&op->d_D, h.size() * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&op->d_refs, ones.size() * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&op->d_terms, sizeof(TermTable))) != cudaSuccess ||
+        (e = cudaMemcpy(op->d_D, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(op->d_refs, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        report_cuda(e, "imexop_create", __FILE__, __LINE__);
+        szb_imexop_destroy(op);
+        return SZB_ECUDA_BASE - (int) e;
+    }
+    *out = op;
+    return 0;
+}
+
+void szb_imexop_destroy(szb_imexop *op)
+{
+    if (!op) return;
+    cudaFree(op->d_D); cudaFree(op->d_refs); cudaFree(op->d_terms); cudaFree(op->d_work);
+    delete op;
+}
+
+szb_bsmbsm szb_imexop_bsmbsm(const szb_imexop *op) { return op->A; }
+
+int szb_imexop_set_scenario(szb_imexop *op, const szb_rholut_imexop_scenario *s)
+{
+    if (!op) return -1;
+    if (!s) return -2;
+    op->scen = *s;
+    build_terms(op->scen, op->h_terms);
+    SZB_CUDA_OK(cudaMemcpy(op->d_terms, &op->h_terms, sizeof(TermTable), cudaMemcpyHostToDevice));
+    // E_factor depends on gamma and Ma as well as the wall data
+    return szb_imexop_set_isothermal(op, &op->iso);
+}
+
+int szb_imexop_set_refs(szb_imexop *op, const szb_rholut_imexop_ref *r,
+                        const szb_rholut_imexop_refld *ld)
+{
+    if (!op) return -1;
+    if (!r) return -2;
+    if (!ld) return -3;
+    const int n = op->n;
+    double *const *ptrs = reinterpret_cast<double *const *>(r);
+    const int *lds = reinterpret_cast<const int *>(ld);
+    std::vector<double> h((size_t) SZB_NREF * n);
+    for (int q = 0; q < SZB_NREF; ++q) {
+        if (!ptrs[q]) return -2;
+        for (int i = 0; i < n; ++i) h[(size_t) q * n + i] = ptrs[q][(size_t) i * lds[q]];
+    }
+    SZB_CUDA_OK(cudaMemcpy(op->d_refs, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int szb_imexop_set_isothermal(szb_imexop *op, const szb_isothermal *iso)
+{
+    if (!op) return -1;
+    if (!iso) return -2;
+    op->iso = *iso;
+    const double g = op->scen.gamma, Ma = op->scen.Ma;
+    // operator_hybrid_isothermal.cpp:448-461
+    op->E_factor[0] = iso->lower_T / (g * (g - 1))
+                    + Ma * Ma / 2 * (iso->lower_u * iso->lower_u + iso->lower_v * iso->lower_v + iso->lower_w * iso->lower_w);
+    op->E_factor[1] = iso->upper_T / (g * (g - 1))
+                    + Ma * Ma / 2 * (iso->upper_u * iso->upper_u + iso->upper_v * iso->upper_v + iso->upper_w * iso->upper_w);
+    op->vel_factor[0][0] = iso->lower_u; op->vel_factor[0][1] = iso->lower_v; op->vel_factor[0][2] = iso->lower_w;
+    op->vel_factor[1][0] = iso->upper_u; op->vel_factor[1][1] = iso->upper_v; op->vel_factor[1][2] = iso->upper_w;
+    return 0;
+}
+
+int szb_imexop_set_nrbc(szb_imexop *op, const double *a, const double *b, const double *c)
+{
+    if (!op) return -1;
+    op->have_a = a != nullptr; op->have_b = b != nullptr; op->have_c = c != nullptr;
+    if (a) std::memcpy(op->nrbc_a, a, sizeof(op->nrbc_a));
+    if (b) std::memcpy(op->nrbc_b, b, sizeof(op->nrbc_b));
+    if (c) std::memcpy(op->nrbc_c, c, sizeof(op->nrbc_c));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI: batched accumulate / pack
+// ---------------------------------------------------------------------------
+int szb_imexop_accumulate_batch(const szb_imexop *op, const double phi[2],
+        int npencil, const double *d_km, const double *d_kn, const int *d_index,
+        const szb_complex *d_in, size_t in_fs, size_t in_ps,
+        const double beta[2],
+        szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream)
+{
+    if (!op) return -1;
+    if (!phi) return -2;
+    if (npencil < 0) return -3;
+    if (!d_km) return -4;
+    if (!d_kn) return -5;
+    if (!d_in) return -7;
+    if (!beta) return -10;
+    if (!d_out) return -11;
+    if (npencil == 0) return 0;
+    if ((const void *) d_in == (const void *) d_out
+        && !(beta[0] == 0.0 && beta[1] == 0.0 && in_fs == out_fs && in_ps == out_ps)) return -11;
+    AccumulateArgs A;
+    A.D = op->d_D; A.refs = op->d_refs; A.terms = op->d_terms;
+    A.n = op->n; A.kl = op->kl; A.ku = op->ku; A.ld = op->ld;
+    A.phi = cplx(phi[0], phi[1]); A.beta = cplx(beta[0], beta[1]);
+    A.km = d_km; A.kn = d_kn; A.index = d_index;
+    A.in = reinterpret_cast<const cplx *>(d_in); A.in_fs = in_fs; A.in_ps = in_ps;
+    A.out = reinterpret_cast<cplx *>(d_out); A.out_fs = out_fs; A.out_ps = out_ps;
+    A.nrbc = (op->have_a ? 1 : 0) | (op->have_b ? 2 : 0) | (op->have_c ? 4 : 0);
+    std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
+    std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
+    std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
+    const size_t smem = sizeof(cplx) * (5 * (size_t) op->n + MAXTERMS);
+    if (smem > 48 * 1024)
+        SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const int threads = op->n >= 128 ? 128 : ((op->n + 31) / 32) * 32;
+    accumulate_kernel<<<npencil, threads, smem, (cudaStream_t) stream>>>(A);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int szb_imexop_pack_batch(const szb_imexop *op, const double phi[2],
+        int npencil, const double *d_km, const double *d_kn,
+        int packf, int with_bc, szb_complex *d_patpt, void *stream)
+{
+    if (!op) return -1;
+    if (!phi) return -2;
+    if (npencil < 0) return -3;
+    if (!d_km) return -4;
+    if (!d_kn) return -5;
+    if (!d_patpt) return -8;
+    if (npencil == 0) return 0;
+    PackArgs A;
+    szb::fill_pack_args(op, phi, d_km, d_kn, packf, with_bc, reinterpret_cast<cplx *>(d_patpt), A);
+    pack_kernel<<<npencil, 256, sizeof(cplx) * MAXTERMS, (cudaStream_t) stream>>>(A);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// szb_internal.hpp -- private definitions shared by the translation units of
+// libsuzerain_b200.so.  Nothing here is part of the C ABI (include/suzerain_b200.h).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/suzerain_b200.h"
+
+#define SZB_CUDA_OK(expr)                                                   \
+    do {                                                                    \
+        cudaError_t szb_err__ = (expr);                                     \
+        if (szb_err__ != cudaSuccess) {                                     \
+            szb::report_cuda(szb_err__, #expr, __FILE__, __LINE__);         \
+            return SZB_ECUDA_BASE - (int) szb_err__;                        \
+        }                                                                   \
+    } while (0)
+
+namespace szb {
+
+void report_cuda(cudaError_t e, const char *what, const char *file, int line);
+void count_launch(unsigned n = 1);
+
+// Term table dimensions (rholut_terms.def)
+enum Field { E = 0, U = 1, V = 2, W = 3, R = 4, NFIELD = 5 };
+enum Oper  { M = 0, D1 = 1, D2 = 2, NOPER = 3 };
+// wave(km,kn) factors and reference-profile ids named as in rholut_terms.def
+namespace wavid { enum { ONE = 0, IKM, IKN, KM2, KN2, KMKN, K2, NWAVE }; }
+namespace refid {
+enum { ux, uy, uz, u2, uxux, uxuy, uxuz, uyuy, uyuz, uzuz, nu, nuux, nuuy,
+       nuuz, nuu2, nuuxux, nuuxuy, nuuxuz, nuuyuy, nuuyuz, nuuzuz,
+       ex_gradrho, ey_gradrho, ez_gradrho, e_divm, e_deltarho,
+       ONE /* pseudo-profile of ones appended to the 26 */ };
+}
+enum { REF_ONE = refid::ONE };
+static_assert(REF_ONE == SZB_NREF, "reference profile count");
+enum { MAXTERMS = 128, NBLOCK = NFIELD * NFIELD * NOPER };
+
+// Flattened term table living in __constant__ memory (one copy per context
+// generation; scenario constants are folded in on the host).
+struct TermTable {
+    int     nterms;
+    double  sc[MAXTERMS];              // scenario factor of each term
+    uint8_t ref[MAXTERMS];             // 0..25 or REF_ONE
+    uint8_t wave[MAXTERMS];            // Wave
+    uint8_t blk_begin[NBLOCK + 1];     // block b = (row*5 + col)*3 + op owns
+                                       // terms [blk_begin[b], blk_begin[b+1])
+};
+
+}  // namespace szb
+
+struct szb_bsplineop {
+    int k, n, nderiv;
+    std::vector<int> kl, ku;
+    int max_kl, max_ku, ld;
+    std::vector<double> knots;         // n + k
+    std::vector<double> greville;      // n
+    std::vector<double> storage;       // (nderiv+1) * ld * n, reference layout
+    const double *D_T(int d) const { return storage.data() + (size_t) d * ld * n + (max_ku - ku[d]); }
+};
+
+struct szb_imexop {
+    // geometry
+    int n, k, kl, ku, ld;              // per-block bandwidths are the max over D_T[0..2]
+    szb_bsmbsm A;                      // S = 5
+    // device tables
+    double *d_D;                       // [3][n][ld]: d_D[(d*n + i)*ld + ku + j - i] = D^(d)[i, j]
+    double *d_refs;                    // [27][n]; row 26 is all ones
+    szb::TermTable *d_terms;           // device copy of the term table
+    szb::TermTable  h_terms;
+    // scenario & boundary data
+    szb_rholut_imexop_scenario scen;
+    szb_isothermal iso;
+    double E_factor[2], vel_factor[2][3];
+    bool   have_a, have_b, have_c;
+    double nrbc_a[25], nrbc_b[25], nrbc_c[25];
+    // scratch for the batched invert: persistent per-CTA LU workspaces
+    mutable void  *d_work;
+    mutable size_t work_bytes;
+    mutable int    work_slots;
+    int sm_count;
+};
