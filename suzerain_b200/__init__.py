@@ -5,8 +5,8 @@ C ABI of ``include/suzerain_b200.h``); this package is the thin host-side mirror
 of the reference's operator interface used by tests and ``bench.py``.
 """
 from . import lib  # noqa: F401
-from .api import (BsplineOp, ImexOp, OperatorHybridIsothermal, SolverSpec,  # noqa: F401
+from .api import (BsplineOp, ImexOp, OperatorHybridIsothermal, OperatorHybridIsothermalDevice, SolverSpec,  # noqa: F401
                   htstretch_breakpoints, wavegrid, wavenumbers)
 
-__all__ = ["lib", "BsplineOp", "ImexOp", "OperatorHybridIsothermal", "SolverSpec",
+__all__ = ["lib", "BsplineOp", "ImexOp", "OperatorHybridIsothermal", "OperatorHybridIsothermalDevice", "SolverSpec",
            "htstretch_breakpoints", "wavegrid", "wavenumbers"]

@@ -328,3 +328,48 @@ class OperatorHybridIsothermal:
                 f"A row {q} for state scalar {q // n}", rc)
         _L.check("szb_operator_invert_mass_plus_scaled_operator", rc)
         return state
+
+
+class OperatorHybridIsothermalDevice:
+    """operator_hybrid_isothermal for a DEVICE-resident state (torch CUDA
+    complex128 tensors in the reference's interleaved layout
+    [5][Ny][Nx_loc][Nz_loc], i.e. shape (npencil, 5, Ny) C-contiguous).  The
+    wavenumber tables and the active / dealiased pencil lists are built once
+    (operator_hybrid_isothermal.cpp:120-134,163-170) and kept on the device."""
+
+    def __init__(self, imexop: ImexOp, grid, spec: SolverSpec | None = None, device=None):
+        import torch
+        self.op, self.grid = imexop, grid
+        self.spec = spec or SolverSpec()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        km, kn, act = wavenumbers(grid)
+        self.npencil = len(km)
+        idx = np.arange(self.npencil, dtype=np.int32)
+        self.h_active, self.h_inactive = idx[act], idx[~act]
+        self.h_km, self.h_kn = km[act], kn[act]
+        self.km = torch.from_numpy(self.h_km).to(self.device)
+        self.kn = torch.from_numpy(self.h_kn).to(self.device)
+        self.active = torch.from_numpy(self.h_active).to(self.device)
+        self.inactive = torch.from_numpy(self.h_inactive).to(self.device)
+        self.nactive = int(act.sum())
+        self.info = torch.zeros(max(self.nactive, 1), dtype=torch.int32, device=self.device)
+
+    def apply_mass_plus_scaled_operator(self, phi, state, stream=None):
+        return self.op.accumulate_batch(phi, self.km, self.kn, state, 0.0, state,
+                                        index=self.active, stream=stream)
+
+    def accumulate_mass_plus_scaled_operator(self, phi, input, beta, output, stream=None):
+        """output: contiguous state (5, npencil, Ny) (suzerain/storage.hpp:267-268)."""
+        n = self.op.n
+        return self.op.accumulate_batch(phi, self.km, self.kn, input, beta, output,
+                                        index=self.active, y_strides=(n * self.npencil, n),
+                                        stream=stream)
+
+    def invert_mass_plus_scaled_operator(self, phi, state, stream=None, ipiv=None, iters=None):
+        n = self.op.n
+        if len(self.h_inactive):
+            rc = _L.load().szb_zero_pencils(len(self.h_inactive), _ptr(self.inactive), 5, n,
+                                            _ptr(state), n, 5 * n, _stream_handle(stream))
+            _L.check("szb_zero_pencils", rc)
+        return self.op.invert_batch(self.spec, phi, self.km, self.kn, state, index=self.active,
+                                    info=self.info, ipiv=ipiv, iters=iters, stream=stream)
