@@ -10,6 +10,7 @@
 //                                            apps/perfect/operator_hybrid_isothermal.cpp:617-686
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 #include "szb_internal.hpp"
 #include "cplx.cuh"
@@ -458,6 +459,19 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     if (nextra > 0 && !d_extra) return -12;
     if (!d_info) return -14;
     if (npencil == 0) return 0;
+
+    // zgbsv with a single right hand side per pencil: the register-window kernel
+    // (invert_window.cu); SZB_INVERT=v1 in the environment forces the generic one.
+    if (spec->method == SZB_SOLVER_ZGBSV && nextra == 0) {
+        static const bool force_v1 = [] { const char *e = std::getenv("SZB_INVERT"); return e && e[0] == 'v' && e[1] == '1'; }();
+        if (!force_v1) {
+            const int rc = invert_window_dispatch(op, phi, npencil, d_km, d_kn, d_index,
+                                                  reinterpret_cast<cplx *>(d_state), field_stride,
+                                                  pencil_stride, d_ipiv, d_info, d_iters,
+                                                  (cudaStream_t) stream);
+            if (rc <= 0) return rc;
+        }
+    }
 
     InvertArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);

@@ -23,6 +23,11 @@ namespace szb {
 
 void report_cuda(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(unsigned n = 1);
+struct cplx;
+int invert_window_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                           const double *d_km, const double *d_kn, const int *d_index,
+                           cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                           int *d_iters, cudaStream_t stream);
 
 // Term table dimensions (rholut_terms.def)
 enum Field { E = 0, U = 1, V = 2, W = 3, R = 4, NFIELD = 5 };

@@ -45,7 +45,7 @@ class Case:
 
 
 def make_case(config="tiny_16x24x16", max_pencils=None, phi=None, seed=synth.SEED,
-              nrbc=None, scenario=None, walls=None, Ny=None, k=None) -> Case:
+              nrbc=None, scenario=None, walls=None, Ny=None, k=None, npencils=None) -> Case:
     Nx, Ny0, Nz, k0, htdelta, one_sided = synth.CONFIGS[config]
     Ny = Ny or Ny0
     k = k or k0
@@ -62,6 +62,11 @@ def make_case(config="tiny_16x24x16", max_pencils=None, phi=None, seed=synth.SEE
         sel = np.unique(np.concatenate([[0, len(km) - 1],
                                         np.linspace(0, len(km) - 1, max_pencils).astype(int)]))
         km, kn = km[sel], kn[sel]
+    if npencils is not None:
+        # synthetic wavenumber list of a requested length (persistent-CTA paths)
+        rng = np.random.default_rng(seed + 1)
+        km = np.concatenate([[0.0], rng.integers(-40, 41, npencils - 1) * (2 * np.pi / synth.LX)])
+        kn = np.concatenate([[0.0], rng.integers(-40, 41, npencils - 1) * (2 * np.pi / synth.LZ)])
     x = synth.state(km, kn, Ny, seed)
     if phi is None:
         phi = complex(-synth.delta_t(Ly) * synth.SMR91_BETA[0], 0.0)
