@@ -460,17 +460,24 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     if (!d_info) return -14;
     if (npencil == 0) return 0;
 
-    // zgbsv with a single right hand side per pencil: the register-window kernel
-    // (invert_window.cu); SZB_INVERT=v1 in the environment forces the generic one.
+    // zgbsv with a single right hand side per pencil: the blocked shared-memory-window
+    // kernel (invert_blocked.cu).  SZB_INVERT=v1 / v2 in the environment selects the
+    // generic global-memory kernel / the register-window kernel (invert_window.cu).
     if (spec->method == SZB_SOLVER_ZGBSV && nextra == 0) {
-        static const bool force_v1 = [] { const char *e = std::getenv("SZB_INVERT"); return e && e[0] == 'v' && e[1] == '1'; }();
-        if (!force_v1) {
-            const int rc = invert_window_dispatch(op, phi, npencil, d_km, d_kn, d_index,
-                                                  reinterpret_cast<cplx *>(d_state), field_stride,
-                                                  pencil_stride, d_ipiv, d_info, d_iters,
-                                                  (cudaStream_t) stream);
-            if (rc <= 0) return rc;
-        }
+        static const int which = [] {
+            const char *e = std::getenv("SZB_INVERT");
+            return (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') ? e[1] - '0' : 3;
+        }();
+        int rc = 1;
+        if (which == 3)
+            rc = invert_blocked_dispatch(op, phi, npencil, d_km, d_kn, d_index,
+                                         reinterpret_cast<cplx *>(d_state), field_stride,
+                                         pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
+        else if (which == 2)
+            rc = invert_window_dispatch(op, phi, npencil, d_km, d_kn, d_index,
+                                        reinterpret_cast<cplx *>(d_state), field_stride,
+                                        pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
+        if (rc <= 0) return rc;
     }
 
     InvertArgs A;
