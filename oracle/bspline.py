@@ -82,6 +82,9 @@ def _basis_derivs(t, k, x, nderiv):
     # Evaluate exactly at the right end point inside the last non-empty span.
     xe = np.array(x, dtype=np.float64)
     for d in range(nderiv + 1):
+        if d > k - 1:                       # derivative order beyond the degree: identically zero
+            out[d] = 0.0
+            continue
         s = spl if d == 0 else spl.derivative(d)
         v = s(xe)
         # extrapolate=False yields nan strictly outside; the right end is included
