@@ -353,7 +353,9 @@ def run_b200(args):
             t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        state_bytes = npen * 5 * n * 16
+        # only active pencils cross the bus (accumulate: input + output up, output down;
+        # invert: state up and down; dealiased pencils are zero-filled on the host)
+        state_bytes = wl.nactive * 5 * n * 16
         e2e = {"value": e2e_s * 1e9 / (wl.gridpoints * world), "unit": "ns/gridpoint/substep",
                "h2d_bytes_per_step": 3 * state_bytes, "d2h_bytes_per_step": 2 * state_bytes,
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,

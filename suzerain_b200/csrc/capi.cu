@@ -2,6 +2,7 @@
 // reference's signatures, the three whole-field virtuals of
 // operator_hybrid_isothermal, and the batched B-spline operator apply.
 #include <cstring>
+#include <new>
 #include <vector>
 
 #include "szb_internal.hpp"
@@ -178,47 +179,160 @@ int szb_rholut_imexop_packf(const double phi[2], double km, double kn,
         const double *a, const double *b, const double *c)
 { return pack_host(1, phi, km, kn, s, r, ld, w, A_T, patpt, a, b, c); }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------
 // Whole-field entry points
+//
+// The state arrives in (ideally pinned) HOST memory.  Only active pencils cross the
+// bus: wave space is cut into chunks of consecutive active kz rows (one strided 2-D
+// copy each), and chunk c+1 is uploaded while chunk c is computed and chunk c-1 is
+// downloaded (three streams, one event pair per chunk).  Dealiased pencils never
+// travel: invert zero-fills them on the host, apply/accumulate leave them alone.
+// Plans, device mirrors, streams and events are cached on the operator context.
 // ---------------------------------------------------------------------------
 namespace {
-struct FieldPlan {
-    std::vector<double> km, kn;       // compacted over active pencils
-    std::vector<int> active_idx, inactive_idx;
-    DevBuf<double> d_km, d_kn;
-    DevBuf<int> d_act, d_inact;
-    int npencil = 0;
-    int zero_zero = -1;               // position of the (0,0) pencil in the active list
+
+struct Chunk {
+    int row0, nrows;          // local kz rows [row0, row0 + nrows)
+    int a0, a1;               // range of the active-pencil list
 };
 
-int make_plan(const szb_wavegrid *g, FieldPlan &P)
+struct FieldCtx {
+    szb_wavegrid g;
+    int nx = 0, nz = 0, xa = 0, npencil = 0, nact = 0;
+    int zero_zero = -1;                     // position of the (0,0) pencil in the active list
+    std::vector<int> active_idx, inactive_idx;
+    std::vector<Chunk> chunks;
+    DevBuf<double> d_km, d_kn;
+    DevBuf<int> d_act, d_info;
+    DevBuf<szb_complex> d_a, d_b;           // interleaved mirror, contiguous-state mirror
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaEvent_t ev_prev = nullptr;
+    ~FieldCtx() {
+        for (auto e : ev_in) cudaEventDestroy(e);
+        for (auto e : ev_done) cudaEventDestroy(e);
+        if (ev_prev) cudaEventDestroy(ev_prev);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_comp) cudaStreamDestroy(s_comp);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+
+int build_ctx(const szb_wavegrid *g, FieldCtx &F)
 {
-    P.npencil = szb_wavegrid_npencils(g);
-    std::vector<double> km(P.npencil), kn(P.npencil);
-    std::vector<int> act(P.npencil);
+    F.g = *g;
+    F.nx = g->dkex - g->dkbx; F.nz = g->dkez - g->dkbz;
+    F.npencil = szb_wavegrid_npencils(g);
+    std::vector<double> km(F.npencil), kn(F.npencil), akm, akn;
+    std::vector<int> act(F.npencil);
     szb_wavegrid_wavenumbers(g, km.data(), kn.data(), act.data());
-    const int nx = g->dkex - g->dkbx;
-    for (int p = 0; p < P.npencil; ++p) {
-        if (act[p]) {
-            const int m = g->dkbx + p % nx, n = g->dkbz + p / nx;
-            if (m == 0 && n == 0) P.zero_zero = (int) P.active_idx.size();
-            P.active_idx.push_back(p); P.km.push_back(km[p]); P.kn.push_back(kn[p]);
-        } else {
-            P.inactive_idx.push_back(p);
+    // active kx form a prefix of every row (non-negative wavenumbers only); check it
+    F.xa = 0;
+    std::vector<int> row_active(F.nz, 0);
+    for (int r = 0; r < F.nz; ++r) {
+        int cnt = 0; bool prefix = true;
+        for (int m = 0; m < F.nx; ++m) {
+            if (act[(size_t) r * F.nx + m]) { if (cnt != m) prefix = false; ++cnt; }
+        }
+        if (!prefix) return -2;
+        if (cnt) { if (F.xa && cnt != F.xa) return -2; F.xa = cnt; row_active[r] = 1; }
+    }
+    std::vector<int> row_a0(F.nz + 1, 0);
+    for (int r = 0; r < F.nz; ++r) {
+        row_a0[r] = (int) F.active_idx.size();
+        for (int m = 0; m < F.nx; ++m) {
+            const int p = r * F.nx + m;
+            if (act[p]) {
+                const int mm = g->dkbx + m, nn = g->dkbz + r;
+                if (mm == 0 && nn == 0) F.zero_zero = (int) F.active_idx.size();
+                F.active_idx.push_back(p); akm.push_back(km[p]); akn.push_back(kn[p]);
+            } else {
+                F.inactive_idx.push_back(p);
+            }
         }
     }
-    SZB_CUDA_OK(P.d_km.alloc(P.km.size())); SZB_CUDA_OK(P.d_kn.alloc(P.kn.size()));
-    SZB_CUDA_OK(P.d_act.alloc(P.active_idx.size())); SZB_CUDA_OK(P.d_inact.alloc(P.inactive_idx.size()));
-    if (!P.km.empty()) {
-        SZB_CUDA_OK(cudaMemcpy(P.d_km.p, P.km.data(), sizeof(double) * P.km.size(), cudaMemcpyHostToDevice));
-        SZB_CUDA_OK(cudaMemcpy(P.d_kn.p, P.kn.data(), sizeof(double) * P.kn.size(), cudaMemcpyHostToDevice));
-        SZB_CUDA_OK(cudaMemcpy(P.d_act.p, P.active_idx.data(), sizeof(int) * P.active_idx.size(), cudaMemcpyHostToDevice));
+    row_a0[F.nz] = (int) F.active_idx.size();
+    F.nact = (int) F.active_idx.size();
+    // chunks of consecutive active rows, about eight per call
+    int nrows_active = 0;
+    for (int r = 0; r < F.nz; ++r) nrows_active += row_active[r];
+    const int per = nrows_active ? (nrows_active + 7) / 8 : 1;
+    for (int r = 0; r < F.nz;) {
+        if (!row_active[r]) { ++r; continue; }
+        int e = r;
+        while (e < F.nz && row_active[e] && e - r < per) ++e;
+        F.chunks.push_back(Chunk{ r, e - r, row_a0[r], row_a0[e] });
+        r = e;
     }
-    if (!P.inactive_idx.empty())
-        SZB_CUDA_OK(cudaMemcpy(P.d_inact.p, P.inactive_idx.data(), sizeof(int) * P.inactive_idx.size(), cudaMemcpyHostToDevice));
+    SZB_CUDA_OK(F.d_km.alloc(akm.size())); SZB_CUDA_OK(F.d_kn.alloc(akn.size()));
+    SZB_CUDA_OK(F.d_act.alloc(F.active_idx.size())); SZB_CUDA_OK(F.d_info.alloc(F.nact + 1));
+    if (F.nact) {
+        SZB_CUDA_OK(cudaMemcpy(F.d_km.p, akm.data(), sizeof(double) * akm.size(), cudaMemcpyHostToDevice));
+        SZB_CUDA_OK(cudaMemcpy(F.d_kn.p, akn.data(), sizeof(double) * akn.size(), cudaMemcpyHostToDevice));
+        SZB_CUDA_OK(cudaMemcpy(F.d_act.p, F.active_idx.data(), sizeof(int) * F.nact, cudaMemcpyHostToDevice));
+    }
+    SZB_CUDA_OK(cudaStreamCreateWithFlags(&F.s_in, cudaStreamNonBlocking));
+    SZB_CUDA_OK(cudaStreamCreateWithFlags(&F.s_comp, cudaStreamNonBlocking));
+    SZB_CUDA_OK(cudaStreamCreateWithFlags(&F.s_out, cudaStreamNonBlocking));
+    F.ev_in.resize(F.chunks.size()); F.ev_done.resize(F.chunks.size());
+    for (auto &e : F.ev_in) SZB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : F.ev_done) SZB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SZB_CUDA_OK(cudaEventCreateWithFlags(&F.ev_prev, cudaEventDisableTiming));
     return 0;
 }
+
+int get_ctx(const szb_imexop *op, const szb_wavegrid *g, FieldCtx **out)
+{
+    FieldCtx *F = static_cast<FieldCtx *>(op->field_ctx);
+    if (F && std::memcmp(&F->g, g, sizeof(*g)) != 0) { delete F; F = nullptr; op->field_ctx = nullptr; }
+    if (!F) {
+        F = new (std::nothrow) FieldCtx();
+        if (!F) return -1;
+        const int rc = build_ctx(g, *F);
+        if (rc) { delete F; return rc; }
+        op->field_ctx = F;
+    }
+    *out = F;
+    return 0;
+}
+
+template <class T> int ensure(DevBuf<T> &b, size_t n)
+{
+    if (b.count >= n && b.p) return 0;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; }
+    SZB_CUDA_OK(b.alloc(n));
+    return 0;
+}
+
+// interleaved state rows [row0, row0+nrows), active prefix only: one strided copy
+int copy_interleaved(const FieldCtx &F, const Chunk &c, size_t N, szb_complex *dst, const szb_complex *src,
+                     cudaMemcpyKind kind, cudaStream_t s)
+{
+    const size_t pitch = sizeof(szb_complex) * N * F.nx, width = sizeof(szb_complex) * N * F.xa;
+    const size_t off = (size_t) c.row0 * F.nx * N;
+    SZB_CUDA_OK(cudaMemcpy2DAsync(dst + off, pitch, src + off, pitch, width, c.nrows, kind, s));
+    return 0;
+}
+
+// contiguous state (field slowest): five strided copies per chunk
+int copy_contiguous(const FieldCtx &F, const Chunk &c, size_t n, size_t fs, szb_complex *dst,
+                    const szb_complex *src, cudaMemcpyKind kind, cudaStream_t s)
+{
+    const size_t pitch = sizeof(szb_complex) * n * F.nx, width = sizeof(szb_complex) * n * F.xa;
+    for (int f = 0; f < 5; ++f) {
+        const size_t off = (size_t) f * fs + (size_t) c.row0 * F.nx * n;
+        SZB_CUDA_OK(cudaMemcpy2DAsync(dst + off, pitch, src + off, pitch, width, c.nrows, kind, s));
+    }
+    return 0;
+}
+
 }  // namespace
+
+void szb::field_ctx_free(void *p) { delete static_cast<FieldCtx *>(p); }
+
+extern "C" {
 
 int szb_operator_apply_mass_plus_scaled_operator(const szb_imexop *op,
         const szb_wavegrid *g, const double phi[2], szb_complex *state)
@@ -227,19 +341,27 @@ int szb_operator_apply_mass_plus_scaled_operator(const szb_imexop *op,
     if (!g) return -2;
     if (!phi) return -3;
     if (!state) return -4;
-    FieldPlan P;
-    int rc = make_plan(g, P);
+    FieldCtx *F;
+    int rc = get_ctx(op, g, &F);
     if (rc) return rc;
-    if (P.npencil == 0) return 0;
-    const size_t N = op->A.N, total = N * P.npencil;
-    DevBuf<szb_complex> d;
-    SZB_CUDA_OK(d.alloc(total));
-    SZB_CUDA_OK(cudaMemcpy(d.p, state, sizeof(szb_complex) * total, cudaMemcpyHostToDevice));
+    if (F->nact == 0) return 0;
+    const size_t N = op->A.N;
+    if ((rc = ensure(F->d_a, N * F->npencil))) return rc;
     const double zero[2] = { 0.0, 0.0 };
-    rc = szb_imexop_accumulate_batch(op, phi, (int) P.active_idx.size(), P.d_km.p, P.d_kn.p,
-                                     P.d_act.p, d.p, op->n, N, zero, d.p, op->n, N, nullptr);
-    if (rc) return rc;
-    SZB_CUDA_OK(cudaMemcpy(state, d.p, sizeof(szb_complex) * total, cudaMemcpyDeviceToHost));
+    for (size_t c = 0; c < F->chunks.size(); ++c) {
+        const Chunk &ch = F->chunks[c];
+        if ((rc = copy_interleaved(*F, ch, N, F->d_a.p, state, cudaMemcpyHostToDevice, F->s_in))) return rc;
+        SZB_CUDA_OK(cudaEventRecord(F->ev_in[c], F->s_in));
+        SZB_CUDA_OK(cudaStreamWaitEvent(F->s_comp, F->ev_in[c], 0));
+        rc = szb_imexop_accumulate_batch(op, phi, ch.a1 - ch.a0, F->d_km.p + ch.a0, F->d_kn.p + ch.a0,
+                                         F->d_act.p + ch.a0, F->d_a.p, op->n, N, zero, F->d_a.p, op->n, N,
+                                         F->s_comp);
+        if (rc) return rc;
+        SZB_CUDA_OK(cudaEventRecord(F->ev_done[c], F->s_comp));
+        SZB_CUDA_OK(cudaStreamWaitEvent(F->s_out, F->ev_done[c], 0));
+        if ((rc = copy_interleaved(*F, ch, N, state, F->d_a.p, cudaMemcpyDeviceToHost, F->s_out))) return rc;
+    }
+    SZB_CUDA_OK(cudaStreamSynchronize(F->s_out));
     return 0;
 }
 
@@ -253,21 +375,34 @@ int szb_operator_accumulate_mass_plus_scaled_operator(const szb_imexop *op,
     if (!input) return -4;
     if (!beta) return -5;
     if (!output) return -6;
-    FieldPlan P;
-    int rc = make_plan(g, P);
+    FieldCtx *F;
+    int rc = get_ctx(op, g, &F);
     if (rc) return rc;
-    if (P.npencil == 0) return 0;
-    const size_t N = op->A.N, n = op->n, total = N * P.npencil;
-    if (out_field_stride < n * (size_t) P.npencil) return -7;
-    const size_t out_total = 4 * out_field_stride + n * (size_t) P.npencil;
-    DevBuf<szb_complex> din, dout;
-    SZB_CUDA_OK(din.alloc(total)); SZB_CUDA_OK(dout.alloc(out_total));
-    SZB_CUDA_OK(cudaMemcpy(din.p, input, sizeof(szb_complex) * total, cudaMemcpyHostToDevice));
-    SZB_CUDA_OK(cudaMemcpy(dout.p, output, sizeof(szb_complex) * out_total, cudaMemcpyHostToDevice));
-    rc = szb_imexop_accumulate_batch(op, phi, (int) P.active_idx.size(), P.d_km.p, P.d_kn.p,
-                                     P.d_act.p, din.p, n, N, beta, dout.p, out_field_stride, n, nullptr);
-    if (rc) return rc;
-    SZB_CUDA_OK(cudaMemcpy(output, dout.p, sizeof(szb_complex) * out_total, cudaMemcpyDeviceToHost));
+    if (F->nact == 0) return 0;
+    const size_t N = op->A.N, n = op->n;
+    if (out_field_stride < n * (size_t) F->npencil) return -7;
+    const size_t out_total = 4 * out_field_stride + n * (size_t) F->npencil;
+    if ((rc = ensure(F->d_a, N * F->npencil))) return rc;
+    if ((rc = ensure(F->d_b, out_total))) return rc;
+    const bool need_out = !(beta[0] == 0.0 && beta[1] == 0.0);
+    for (size_t c = 0; c < F->chunks.size(); ++c) {
+        const Chunk &ch = F->chunks[c];
+        if ((rc = copy_interleaved(*F, ch, N, F->d_a.p, input, cudaMemcpyHostToDevice, F->s_in))) return rc;
+        if (need_out &&
+            (rc = copy_contiguous(*F, ch, n, out_field_stride, F->d_b.p, output, cudaMemcpyHostToDevice, F->s_in)))
+            return rc;
+        SZB_CUDA_OK(cudaEventRecord(F->ev_in[c], F->s_in));
+        SZB_CUDA_OK(cudaStreamWaitEvent(F->s_comp, F->ev_in[c], 0));
+        rc = szb_imexop_accumulate_batch(op, phi, ch.a1 - ch.a0, F->d_km.p + ch.a0, F->d_kn.p + ch.a0,
+                                         F->d_act.p + ch.a0, F->d_a.p, n, N, beta, F->d_b.p,
+                                         out_field_stride, n, F->s_comp);
+        if (rc) return rc;
+        SZB_CUDA_OK(cudaEventRecord(F->ev_done[c], F->s_comp));
+        SZB_CUDA_OK(cudaStreamWaitEvent(F->s_out, F->ev_done[c], 0));
+        if ((rc = copy_contiguous(*F, ch, n, out_field_stride, output, F->d_b.p, cudaMemcpyDeviceToHost, F->s_out)))
+            return rc;
+    }
+    SZB_CUDA_OK(cudaStreamSynchronize(F->s_out));
     return 0;
 }
 
@@ -283,43 +418,56 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
     if (nconstraints < 0) return -6;
     if (nconstraints > 0 && !ic0) return -7;
     if (first_bad_pencil) *first_bad_pencil = -1;
-    FieldPlan P;
-    int rc = make_plan(g, P);
+    FieldCtx *F;
+    int rc = get_ctx(op, g, &F);
     if (rc) return rc;
-    if (P.npencil == 0) return 0;
-    if (nconstraints > 0 && P.zero_zero < 0) return -6;      // must own the (0,0) mode (:580-587)
-    const size_t N = op->A.N, total = N * P.npencil;
-    const int nact = (int) P.active_idx.size();
-    DevBuf<szb_complex> d, dic; DevBuf<int> dinfo;
-    SZB_CUDA_OK(d.alloc(total)); SZB_CUDA_OK(dinfo.alloc(nact + 1));
-    SZB_CUDA_OK(cudaMemcpy(d.p, state, sizeof(szb_complex) * total, cudaMemcpyHostToDevice));
-    rc = szb_zero_pencils((int) P.inactive_idx.size(), P.d_inact.p, 5, op->n, d.p, op->n, N, nullptr);
-    if (rc) return rc;
-    rc = szb_imexop_invert_batch(op, spec, phi, nact, P.d_km.p, P.d_kn.p, P.d_act.p, d.p, op->n, N,
-                                 0, nullptr, nullptr, dinfo.p, nullptr, nullptr);
-    if (rc) return rc;
-    std::vector<int> info(nact + 1, 0);
+    if (F->npencil == 0) return 0;
+    if (nconstraints > 0 && F->zero_zero < 0) return -6;     // must own the (0,0) mode (:580-587)
+    const size_t N = op->A.N;
+    if ((rc = ensure(F->d_a, N * F->npencil))) return rc;
+    std::vector<int> info(F->nact + 1, 0);
+
+    DevBuf<szb_complex> scratch, dic;
     if (nconstraints > 0) {
-        // Constraint right hand sides ride on the (0,0) pencil's operator: solve
-        // that one pencil again on a scratch copy with the constraints attached
-        // (same factorisation arithmetic; results for the state are discarded).
-        DevBuf<szb_complex> scratch;
+        // Constraint right hand sides ride on the (0,0) pencil's operator: that one pencil is
+        // solved on a scratch copy with the constraints attached (same factorisation
+        // arithmetic; the scratch state is discarded).  Issued first so that it overlaps
+        // the bulk upload.
         SZB_CUDA_OK(scratch.alloc(N));
         SZB_CUDA_OK(dic.alloc(N * (size_t) nconstraints));
-        SZB_CUDA_OK(cudaMemcpy(scratch.p, state + N * (size_t) P.active_idx[P.zero_zero],
-                               sizeof(szb_complex) * N, cudaMemcpyHostToDevice));
-        SZB_CUDA_OK(cudaMemcpy(dic.p, ic0, sizeof(szb_complex) * N * nconstraints, cudaMemcpyHostToDevice));
-        rc = szb_imexop_invert_batch(op, spec, phi, 1, P.d_km.p + P.zero_zero, P.d_kn.p + P.zero_zero,
+        SZB_CUDA_OK(cudaMemcpyAsync(scratch.p, state + N * (size_t) F->active_idx[F->zero_zero],
+                                    sizeof(szb_complex) * N, cudaMemcpyHostToDevice, F->s_comp));
+        SZB_CUDA_OK(cudaMemcpyAsync(dic.p, ic0, sizeof(szb_complex) * N * nconstraints,
+                                    cudaMemcpyHostToDevice, F->s_comp));
+        rc = szb_imexop_invert_batch(op, spec, phi, 1, F->d_km.p + F->zero_zero, F->d_kn.p + F->zero_zero,
                                      nullptr, scratch.p, op->n, N, nconstraints, dic.p, nullptr,
-                                     dinfo.p + nact, nullptr, nullptr);
+                                     F->d_info.p + F->nact, nullptr, F->s_comp);
         if (rc) return rc;
-        SZB_CUDA_OK(cudaMemcpy(ic0, dic.p, sizeof(szb_complex) * N * nconstraints, cudaMemcpyDeviceToHost));
+        SZB_CUDA_OK(cudaMemcpyAsync(ic0, dic.p, sizeof(szb_complex) * N * nconstraints,
+                                    cudaMemcpyDeviceToHost, F->s_comp));
     }
-    SZB_CUDA_OK(cudaMemcpy(info.data(), dinfo.p, sizeof(int) * (nact + (nconstraints > 0)), cudaMemcpyDeviceToHost));
-    SZB_CUDA_OK(cudaMemcpy(state, d.p, sizeof(szb_complex) * total, cudaMemcpyDeviceToHost));
-    for (int p = 0; p < nact + (nconstraints > 0); ++p) {
+    for (size_t c = 0; c < F->chunks.size(); ++c) {
+        const Chunk &ch = F->chunks[c];
+        if ((rc = copy_interleaved(*F, ch, N, F->d_a.p, state, cudaMemcpyHostToDevice, F->s_in))) return rc;
+        SZB_CUDA_OK(cudaEventRecord(F->ev_in[c], F->s_in));
+        SZB_CUDA_OK(cudaStreamWaitEvent(F->s_comp, F->ev_in[c], 0));
+        rc = szb_imexop_invert_batch(op, spec, phi, ch.a1 - ch.a0, F->d_km.p + ch.a0, F->d_kn.p + ch.a0,
+                                     F->d_act.p + ch.a0, F->d_a.p, op->n, N, 0, nullptr, nullptr,
+                                     F->d_info.p + ch.a0, nullptr, F->s_comp);
+        if (rc) return rc;
+        SZB_CUDA_OK(cudaEventRecord(F->ev_done[c], F->s_comp));
+        SZB_CUDA_OK(cudaStreamWaitEvent(F->s_out, F->ev_done[c], 0));
+        if ((rc = copy_interleaved(*F, ch, N, state, F->d_a.p, cudaMemcpyDeviceToHost, F->s_out))) return rc;
+    }
+    // dealiased / Nyquist pencils are zero-filled (:632-637): on the host, they never travel
+    for (int p : F->inactive_idx) std::memset(state + N * (size_t) p, 0, sizeof(szb_complex) * N);
+    SZB_CUDA_OK(cudaStreamSynchronize(F->s_comp));
+    SZB_CUDA_OK(cudaMemcpy(info.data(), F->d_info.p, sizeof(int) * (F->nact + (nconstraints > 0)),
+                           cudaMemcpyDeviceToHost));
+    SZB_CUDA_OK(cudaStreamSynchronize(F->s_out));
+    for (int p = 0; p < F->nact + (nconstraints > 0); ++p) {
         if (info[p]) {
-            if (first_bad_pencil) *first_bad_pencil = p < nact ? P.active_idx[p] : P.active_idx[P.zero_zero];
+            if (first_bad_pencil) *first_bad_pencil = p < F->nact ? F->active_idx[p] : F->active_idx[F->zero_zero];
             return info[p];
         }
     }

@@ -67,14 +67,14 @@ static void build_terms(const szb_rholut_imexop_scenario &s, TermTable &tt)
 // ---------------------------------------------------------------------------
 // accumulate: out <- (M + phi L) in + beta out, one CTA per pencil.
 //
-// Layout in shared memory: the five input pencils (5*n complex) and the
-// per-term coefficients alpha_t = phi * sc_t * wave_t(km, kn).
-// Each thread owns collocation points y = tid, tid + blockDim, ...:
-//   P[d][j] = sum_r D^(d)[y, y - ku + r] * in_j[y - ku + r]     (15 banded dots)
-//   out_i   = beta out_i + sum_{blocks (i,j,d)} (sum_t alpha_t ref_t[y]) P[d][j]
-//             + P[M][i]                                   (mass added last)
-// The block structure is unrolled at compile time from rholut_terms.def so
-// P and the accumulators stay in registers.
+// Shared memory holds the five input pencils (5*n complex), the 15 banded products
+// and the per-term coefficients alpha_t = phi * sc_t * wave_t(km, kn):
+//   P[d][j](y) = sum_r D^(d)[y, y - ku + r] * in_j[y - ku + r]      one thread per (j, y)
+//   out_i(y)   = beta out_i + sum_{blocks (i,j,d)} (sum_t alpha_t ref_t[y]) P[d][j]
+//                + P[M][i]                                (mass added last)   one thread per (i, y)
+// The block structure of each row is unrolled at compile time from rholut_terms.def.
+// HBM traffic is the algorithmic minimum: every state element is read once and written
+// once (plus one read of the output when beta != 0); operators and profiles stay in L1/L2.
 // ---------------------------------------------------------------------------
 struct AccumulateArgs {
     const double *D;        // [3][ld][n]  (r-major: D[(d*ld + r)*n + y])
@@ -89,15 +89,46 @@ struct AccumulateArgs {
     double a[25], b[25], c[25];
 };
 
-__global__ void __launch_bounds__(128)
+// One output row of (M + phi L) at collocation point y, statically specialised on the
+// equation ROW: only that row's terms of rholut_terms.def survive constant folding.
+template <int ROW>
+__device__ __forceinline__ cplx accumulate_row(const double *refs, int n, int y, const cplx *s_alpha,
+                                               const cplx *s_P)
+{
+    cplx acc(0.0, 0.0), c(0.0, 0.0);
+    int t = 0, cur = -1, ccol = 0, cop = 0;
+#define SZB_FLUSH() do { if (cur >= 0) acc += c * s_P[(size_t) (cop * 5 + ccol) * n + y]; } while (0)
+#define SZB_TERM(row, col, op, ref, wave, scen)                                  \
+    if (szb::row == ROW) {                                                       \
+        if ((szb::col) * 3 + szb::op != cur) {                                   \
+            SZB_FLUSH();                                                         \
+            cur = (szb::col) * 3 + szb::op; ccol = szb::col; cop = szb::op;      \
+            c = cplx(0.0, 0.0);                                                  \
+        }                                                                        \
+        c += s_alpha[t] * __ldg(refs + (size_t) refid::ref * n + y);             \
+    }                                                                            \
+    ++t;
+#include "rholut_terms.def"
+#undef SZB_TERM
+    SZB_FLUSH();
+#undef SZB_FLUSH
+    return acc;
+}
+
+// Work is split twice over the CTA: first one thread per (field j, point y) forms the
+// three banded products D^(0..2) in_j at y into shared memory, then one thread per
+// (equation i, point y) combines them with the reference profiles.
+__global__ void __launch_bounds__(256)
 accumulate_kernel(const AccumulateArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = A.n;
     cplx *s_in    = reinterpret_cast<cplx *>(smem_raw);            // [5][n]
-    cplx *s_alpha = s_in + 5 * A.n;                                // [nterms]
+    cplx *s_P     = s_in + 5 * n;                                  // [3][5][n]
+    cplx *s_alpha = s_P + 15 * n;                                  // [MAXTERMS]
+    cplx *s_top   = s_alpha + MAXTERMS;                            // [5] phi L in at the upper boundary
 
     const int p = blockIdx.x;
-    const int n = A.n;
     const double km = A.km[p], kn = A.kn[p];
     const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
     const cplx *in = A.in + slot * A.in_ps;
@@ -108,122 +139,74 @@ accumulate_kernel(const AccumulateArgs A)
         s_in[e] = in[(size_t) f * A.in_fs + y];
     }
     const int nterms = A.terms->nterms;
-    for (int t = threadIdx.x; t < nterms; t += blockDim.x) {
-        const cplx w = wave_factor(A.terms->wave[t], km, kn);
-        s_alpha[t] = A.phi * (w * A.terms->sc[t]);
+    for (int t = threadIdx.x; t < nterms; t += blockDim.x)
+        s_alpha[t] = A.phi * (wave_factor(A.terms->wave[t], km, kn) * A.terms->sc[t]);
+    __syncthreads();
+
+    // ---- banded products: P[d][j](y) = sum_r D^(d)[y, y-ku+r] in_j[y-ku+r] ----
+    for (int e = threadIdx.x; e < 5 * n; e += blockDim.x) {
+        const int j = e / n, y = e - j * n;
+        cplx P0(0.0, 0.0), P1(0.0, 0.0), P2(0.0, 0.0);
+        const int r0 = max(0, A.ku - y), r1 = min(A.ld, n - y + A.ku);
+        const cplx *x = s_in + j * n + (y - A.ku);
+        const double *D0 = A.D + y, *D1 = D0 + (size_t) A.ld * n, *D2 = D1 + (size_t) A.ld * n;
+        for (int r = r0; r < r1; ++r) {
+            const cplx v = x[r];
+            addmul(P0, v, __ldg(D0 + (size_t) r * n));
+            addmul(P1, v, __ldg(D1 + (size_t) r * n));
+            addmul(P2, v, __ldg(D2 + (size_t) r * n));
+        }
+        s_P[(size_t) (0 * 5 + j) * n + y] = P0;
+        s_P[(size_t) (1 * 5 + j) * n + y] = P1;
+        s_P[(size_t) (2 * 5 + j) * n + y] = P2;
     }
     __syncthreads();
 
+    // ---- rows: out_i = beta out_i + phi L in (+ NRBC) + M in_i, mass added last ----
     const bool beta_zero = is_zero(A.beta);
     const bool nrbc = A.nrbc != 0;
-
-    for (int y = threadIdx.x; y < n; y += blockDim.x) {
-        // --- 15 banded products ---
-        cplx P[3][5];
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) P[d][j] = cplx(0.0, 0.0);
-        const int r0 = max(0, A.ku - y), r1 = min(A.ld, n - y + A.ku);
-        for (int r = r0; r < r1; ++r) {
-            const int x = y - A.ku + r;
-            const double m0 = A.D[(size_t) (0 * A.ld + r) * n + y];
-            const double m1 = A.D[(size_t) (1 * A.ld + r) * n + y];
-            const double m2 = A.D[(size_t) (2 * A.ld + r) * n + y];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const cplx v = s_in[j * n + x];
-                addmul(P[0][j], v, m0);
-                addmul(P[1][j], v, m1);
-                addmul(P[2][j], v, m2);
-            }
+    for (int e = threadIdx.x; e < 5 * n; e += blockDim.x) {
+        const int i = e / n, y = e - i * n;
+        cplx phiL;
+        switch (i) {
+        case 0:  phiL = accumulate_row<0>(A.refs, n, y, s_alpha, s_P); break;
+        case 1:  phiL = accumulate_row<1>(A.refs, n, y, s_alpha, s_P); break;
+        case 2:  phiL = accumulate_row<2>(A.refs, n, y, s_alpha, s_P); break;
+        case 3:  phiL = accumulate_row<3>(A.refs, n, y, s_alpha, s_P); break;
+        default: phiL = accumulate_row<4>(A.refs, n, y, s_alpha, s_P); break;
         }
-
-        // --- reference profiles at y ---
-        double rf[REF_ONE + 1];
-#pragma unroll
-        for (int q = 0; q <= REF_ONE; ++q) rf[q] = A.refs[(size_t) q * n + y];
-
-        const bool top = nrbc && (y == n - 1);
-        cplx acc[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            acc[i] = (beta_zero || top) ? cplx(0.0, 0.0)
-                                        : A.beta * out[(size_t) i * A.out_fs + y];
-        }
-
-        // --- block contributions, statically unrolled ---
-        {
-            int t = 0, cur = -1, crow = 0, ccol = 0, cop = 0;
-            cplx c(0.0, 0.0);
-#define SZB_FLUSH() do { if (cur >= 0) acc[crow] += c * P[cop][ccol]; } while (0)
-#define SZB_TERM(row, col, op, ref, wave, scen)                              \
-            if ((szb::row * 5 + szb::col) * 3 + szb::op != cur) {            \
-                SZB_FLUSH();                                                 \
-                cur = (szb::row * 5 + szb::col) * 3 + szb::op;               \
-                crow = szb::row; ccol = szb::col; cop = szb::op;             \
-                c = cplx(0.0, 0.0);                                          \
-            }                                                                \
-            c += s_alpha[t] * rf[refid::ref]; ++t;
-#include "rholut_terms.def"
-#undef SZB_TERM
-            SZB_FLUSH();
-#undef SZB_FLUSH
-        }
-
-        cplx phiL[5];
-        if (top) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                phiL[i] = acc[i];
-                acc[i] = beta_zero ? acc[i]
-                                   : A.beta * out[(size_t) i * A.out_fs + y] + acc[i];
-            }
-        }
-        // mass last
-#pragma unroll
-        for (int i = 0; i < 5; ++i) acc[i] += P[0][i];
-
-        if (top) {
-            // NRBC upper-boundary correction (rholut_imexop.c:510-545)
-            cplx tt[5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) tt[i] = cplx(0.0, 0.0);
-            const cplx ikmphi = cplx(0.0, km) * A.phi;
-            const cplx iknphi = cplx(0.0, kn) * A.phi;
+        cplx *o = out + (size_t) i * A.out_fs + y;
+        cplx acc = beta_zero ? phiL : A.beta * (*o) + phiL;
+        acc += s_P[(size_t) i * n + y];                              // M in_i (d = 0, j = i)
+        if (nrbc && y == n - 1) s_top[i] = phiL;
+        *o = acc;
+    }
+    if (nrbc) {
+        // upper-boundary correction (rholut_imexop.c:510-545):
+        //   t = -i phi (km a + kn b) in(top) - c (phi L in)(top)
+        __syncthreads();
+        const int i = threadIdx.x;
+        if (i < 5) {
+            cplx tt(0.0, 0.0);
+            const cplx ikmphi = cplx(0.0, km) * A.phi, iknphi = cplx(0.0, kn) * A.phi;
             if (A.nrbc & 1) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    cplx s(0.0, 0.0);
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.a[i + 5 * j];
-                    tt[i] -= ikmphi * s;
-                }
+                cplx s(0.0, 0.0);
+                for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.a[i + 5 * j];
+                tt -= ikmphi * s;
             }
             if (A.nrbc & 2) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    cplx s(0.0, 0.0);
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.b[i + 5 * j];
-                    tt[i] -= iknphi * s;
-                }
+                cplx s(0.0, 0.0);
+                for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.b[i + 5 * j];
+                tt -= iknphi * s;
             }
             if (A.nrbc & 4) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    cplx s(0.0, 0.0);
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) s += phiL[j] * A.c[i + 5 * j];
-                    tt[i] -= s;
-                }
+                cplx s(0.0, 0.0);
+                for (int j = 0; j < 5; ++j) s += s_top[j] * A.c[i + 5 * j];
+                tt -= s;
             }
-#pragma unroll
-            for (int i = 0; i < 5; ++i) acc[i] += tt[i];
+            cplx *o = out + (size_t) i * A.out_fs + (n - 1);
+            *o = *o + tt;
         }
-
-#pragma unroll
-        for (int i = 0; i < 5; ++i) out[(size_t) i * A.out_fs + y] = acc[i];
     }
 }
 
@@ -279,7 +262,7 @@ int szb_imexop_create(const szb_bsplineop *w, szb_imexop **out)
     op->n = w->n; op->k = w->k; op->kl = w->max_kl; op->ku = w->max_ku; op->ld = w->ld;
     op->A = szb_bsmbsm_construct(5, w->n, w->max_kl, w->max_ku);
     op->d_D = nullptr; op->d_refs = nullptr; op->d_terms = nullptr;
-    op->d_work = nullptr; op->work_bytes = 0; op->work_slots = 0;
+    op->d_work = nullptr; op->work_bytes = 0; op->work_slots = 0; op->field_ctx = nullptr;
     op->have_a = op->have_b = op->have_c = false;
     std::memset(&op->iso, 0, sizeof(op->iso));
     op->iso.enforce_lower = 1; op->iso.enforce_upper = 1;
@@ -318,6 +301,7 @@ int szb_imexop_create(const szb_bsplineop *w, szb_imexop **out)
 void szb_imexop_destroy(szb_imexop *op)
 {
     if (!op) return;
+    if (op->field_ctx) szb::field_ctx_free(op->field_ctx);
     cudaFree(op->d_D); cudaFree(op->d_refs); cudaFree(op->d_terms); cudaFree(op->d_work);
     delete op;
 }
@@ -410,11 +394,11 @@ int szb_imexop_accumulate_batch(const szb_imexop *op, const double phi[2],
     std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
     std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
     std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
-    const size_t smem = sizeof(cplx) * (5 * (size_t) op->n + MAXTERMS);
+    const size_t smem = sizeof(cplx) * (20 * (size_t) op->n + MAXTERMS + 8);
+    if (smem > 227 * 1024) return -1;
     if (smem > 48 * 1024)
         SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    const int threads = op->n >= 128 ? 128 : ((op->n + 31) / 32) * 32;
-    accumulate_kernel<<<npencil, threads, smem, (cudaStream_t) stream>>>(A);
+    accumulate_kernel<<<npencil, 256, smem, (cudaStream_t) stream>>>(A);
     count_launch();
     SZB_CUDA_OK(cudaGetLastError());
     return 0;

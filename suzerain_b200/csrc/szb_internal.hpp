@@ -23,6 +23,7 @@ namespace szb {
 
 void report_cuda(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(unsigned n = 1);
+void field_ctx_free(void *p);      // capi.cu: cached whole-field plan of an operator context
 struct cplx;
 int invert_window_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                            const double *d_km, const double *d_kn, const int *d_index,
@@ -90,5 +91,6 @@ struct szb_imexop {
     mutable void  *d_work;
     mutable size_t work_bytes;
     mutable int    work_slots;
+    mutable void  *field_ctx;          // cached whole-field plan (capi.cu)
     int sm_count;
 };

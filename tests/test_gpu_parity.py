@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle on the
 same seeded inputs.  Tolerances are north_star's: relative max-norm <= 1e-12
 after one operator application / solve, pivot choices identical."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -201,3 +203,164 @@ def test_invert_singular_reports_info(dev):
     # wall columns carry the enforcer's unit diagonal; the first interior column is singular
     assert np.all(got["info"] == pc.oracle_invert(case2, "zgbsv")["info"])       # zgbtrf's info
     assert np.allclose(got["x"], case.x.reshape(len(case.km), -1))      # state untouched
+
+
+# ---------------------------------------------------------------------------
+# the reference's own golden vectors replayed on the GPU (tests/golden/*.json)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("cplx", [False, True])
+def test_golden_bsmbsm_solve_on_gpu(dev, cplx):
+    """tests/test_bsmbsm.cpp:801-966 (solve_real / solve_complex): pack, gbsv, unpermute."""
+    import torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import lib as L
+    import test_oracle as to
+    from oracle import port
+    g, A, papt = to.golden_system(cplx)
+    N, KL, KU = A["N"], A["KL"], A["KU"]
+    lib = L.load()
+    ab = torch.from_numpy(np.where(np.isnan(papt), 0, papt).copy()).to(dev)        # (N, 2KL+KU+1)
+    BR = np.array(g["BR"])
+    rhs = ((-BR + 1j * BR) if cplx else BR.astype(complex)).reshape(1, N)
+    x_in = torch.from_numpy(rhs.copy()).to(dev)
+    b = torch.zeros_like(x_in)
+    one, zero = (C.c_double * 2)(1.0, 0.0), (C.c_double * 2)(0.0, 0.0)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    L.check("zaPxpby", lib.szb_bsmbsm_zaPxpby_batch(b"N", A["S"], A["n"], one, p(x_in), zero, p(b), 1, s))
+    ipiv = torch.zeros(N, dtype=torch.int32, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    ld = 2 * KL + KU + 1
+    L.check("zgbtrf", lib.szb_zgbtrf_batch(N, KL, KU, p(ab), ld, N * ld, p(ipiv), p(info), 1, s))
+    L.check("zgbtrs", lib.szb_zgbtrs_batch(b"N", N, KL, KU, 1, p(ab), ld, N * ld, p(ipiv), p(b), N, N, 1, s))
+    x = torch.zeros_like(b)
+    L.check("zaPxpby", lib.szb_bsmbsm_zaPxpby_batch(b"T", A["S"], A["n"], one, p(b), zero, p(x), 1, s))
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    XR = np.array(g["XR"])
+    want = (1 + 1j) * XR if cplx else XR
+    assert np.abs(x.cpu().numpy().reshape(-1) - want).max() <= 1.8e4 * np.finfo(float).eps * np.abs(XR).max()
+    # pivots as LAPACK's (pinned through the oracle port, itself pinned to SciPy's zgbtrf)
+    _, ipiv_want, _ = port.zgbtf2(np.where(np.isnan(papt), 0, papt).T.copy(), N, KL, KU)
+    assert np.array_equal(ipiv.cpu().numpy(), ipiv_want)
+
+
+def test_golden_bsplineop_actions_on_gpu(dev):
+    """tests/test_bsplineop.cpp:697-742: k = 8 operator actions through the batched apply."""
+    import json, os, torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import lib as L
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bsplineop_colloc.json")))["septic"]
+    op = sz.BsplineOp.from_breakpoints(8, np.array(g["breakpoints"]), nderiv=2)
+    lib = L.load()
+    for act in g["actions"]:
+        x = torch.from_numpy(np.array(act["x"]).reshape(act["nrhs"], -1).astype(np.complex128)).to(dev)
+        y = torch.zeros_like(x)
+        a = (C.c_double * 2)(act["alpha"], 0.0)
+        z = (C.c_double * 2)(0.0, 0.0)
+        rc = lib.szb_bsplineop_accumulate_complex_batch(op.handle, act["d"], act["nrhs"], a,
+                                                        C.c_void_p(x.data_ptr()), op.n, z,
+                                                        C.c_void_p(y.data_ptr()), op.n,
+                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        L.check("bsplineop_accumulate", rc)
+        torch.cuda.synchronize()
+        want = np.array(act["y"]).reshape(act["nrhs"], -1)
+        got = y.cpu().numpy()
+        assert np.abs(got.imag).max() == 0
+        assert np.abs(got.real - want).max() <= 1000 * np.finfo(float).eps * np.abs(want).max()
+
+
+# ---------------------------------------------------------------------------
+# whole-field HOST-pointer entry points (the three virtuals of operator_hybrid_isothermal)
+# ---------------------------------------------------------------------------
+def _field_case():
+    import suzerain_b200 as sz
+    from suzerain_b200 import synth
+    case = pc.make_case("tiny_16x24x16")
+    g = sz.wavegrid(16, 16, synth.LX, synth.LZ)
+    km, kn, act = sz.wavenumbers(g)
+    state = synth.state(km, kn, 24, synth.SEED)                       # (npencil, 5, n), dealiased pencils non-zero
+    return case, g, km, kn, act, state
+
+
+@pytest.mark.parametrize("solver", ["zgbsv", "zcgbsvx"])
+def test_whole_field_invert_host_api(dev, solver):
+    import suzerain_b200 as sz
+    case, g, km, kn, act, state = _field_case()
+    op = pc.make_imexop(case)
+    H = sz.OperatorHybridIsothermal(op, g, sz.SolverSpec(method=solver))
+    rng = np.random.default_rng(5)
+    N = 5 * case.n
+    ic0 = rng.standard_normal((10, N)) + 1j * rng.standard_normal((10, N))     # treatment_constraint.cpp:129-166
+    got, got_ic = state.copy(), ic0.copy()
+    H.invert_mass_plus_scaled_operator(case.phi, got, ic0=got_ic)
+    P = pc.oracle_problem(case)
+    flat = state.reshape(len(km), -1)
+    want = np.zeros_like(flat)                                          # dealiased pencils zero-filled (:632-637)
+    zz = int(np.flatnonzero((km[act] == 0) & (kn[act] == 0))[0])
+    extra = np.zeros((act.sum(), 10, N), dtype=complex)
+    extra[zz] = ic0
+    r = P.invert(solver, case.phi, km[act], kn[act], flat[act], extra=extra)
+    want[act] = r["x"]
+    assert pc.relmax(got.reshape(len(km), -1), want) <= TOL
+    assert np.all(got.reshape(len(km), -1)[~act] == 0)
+    assert pc.relmax(got_ic, r["extra"][zz]) <= TOL                    # constraints ride on the (0,0) factorisation
+
+
+def test_whole_field_apply_and_accumulate_host_api(dev):
+    import suzerain_b200 as sz
+    case, g, km, kn, act, state = _field_case()
+    op = pc.make_imexop(case)
+    H = sz.OperatorHybridIsothermal(op, g)
+    P = pc.oracle_problem(case)
+    flat = state.reshape(len(km), -1)
+    # apply: in place, dealiased pencils untouched (operator_hybrid_isothermal.cpp:164-169)
+    got = state.copy()
+    H.apply_mass_plus_scaled_operator(case.phi, got)
+    want = flat.copy()
+    want[act] = P.accumulate(case.phi, km[act], kn[act], flat[act])
+    assert pc.relmax(got.reshape(len(km), -1), want) <= TOL
+    # accumulate: contiguous-state output (field slowest), beta != 0, padded field stride
+    npen, n = len(km), case.n
+    fs = npen * n + 7
+    rng = np.random.default_rng(9)
+    out0 = rng.standard_normal(4 * fs + npen * n) + 1j * rng.standard_normal(4 * fs + npen * n)
+    out = out0.copy()
+    beta = 0.25 + 0.5j
+    H.accumulate_mass_plus_scaled_operator(case.phi, state, beta, out, fs)
+    y0 = np.stack([out0[f * fs: f * fs + npen * n].reshape(npen, n) for f in range(5)], axis=1).reshape(npen, -1)
+    wanty = y0.copy()
+    wanty[act] = P.accumulate(case.phi, km[act], kn[act], flat[act], beta=beta, y=y0[act])
+    goty = np.stack([out[f * fs: f * fs + npen * n].reshape(npen, n) for f in range(5)], axis=1).reshape(npen, -1)
+    assert pc.relmax(goty, wanty) <= TOL
+    for f in range(4):                                                  # padding between fields untouched
+        assert np.array_equal(out[f * fs + npen * n:(f + 1) * fs], out0[f * fs + npen * n:(f + 1) * fs])
+
+
+def test_hundred_substeps_track_the_oracle(dev, tiny):
+    """north_star: <= 1e-9 relative after 100 time steps.  Drive 100 L-substeps
+    (accumulate with the SMR91 alpha, exchange, invert with the SMR91 beta) on the GPU
+    and through the oracle from the same state."""
+    import torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import synth
+    op = pc.make_imexop(tiny)
+    km = torch.from_numpy(tiny.km).to(dev); kn = torch.from_numpy(tiny.kn).to(dev)
+    a = torch.from_numpy(tiny.x.copy()).to(dev); tmp = torch.zeros_like(a)
+    info = torch.zeros(len(tiny.km), dtype=torch.int32, device=dev)
+    P = pc.oracle_problem(tiny)
+    ha = tiny.x.reshape(len(tiny.km), -1).copy(); htmp = np.zeros_like(ha)
+    dt = synth.delta_t(2.0)
+    spec = sz.SolverSpec("zgbsv")
+    for step in range(100):
+        i = step % 3
+        pa, beta, pi = dt * synth.SMR91_ALPHA[i], 1e-3 * dt * synth.SMR91_ZETA[i], -dt * synth.SMR91_BETA[i]
+        op.accumulate_batch(pa, km, kn, a, beta, tmp)
+        a, tmp = tmp, a
+        op.invert_batch(spec, pi, km, kn, a, info=info)
+        htmp = P.accumulate(complex(pa), tiny.km, tiny.kn, ha, beta=complex(beta), y=htmp)
+        ha, htmp = htmp, ha
+        ha = P.invert("zgbsv", complex(pi), tiny.km, tiny.kn, ha, nthreads=4)["x"]
+    torch.cuda.synchronize()
+    assert int(info.abs().max()) == 0
+    assert pc.relmax(a.cpu().numpy().reshape(len(tiny.km), -1), ha) <= 1e-9
