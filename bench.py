@@ -377,6 +377,12 @@ def run_b200(args):
     acc_bytes = (3 if True else 2) * 16 * N * wl.nactive
     inv_gbs = inv_bytes / (inv_ms * 1e-3) / 1e9
     acc_gbs = acc_bytes / (acc_ms * 1e-3) / 1e9
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl.name, {})
+    except Exception:
+        pass
+    tr = lambda k: (traffic[k]["read"] + traffic[k]["write"]) if (k in traffic and args.solver == "zgbsv") else None
     KL = op.KL
     KU = op.KU
     lu_flop = 8.0 * N * KL * (KL + KU) + 8.0 * N * (2 * KL + KU)
@@ -387,11 +393,12 @@ def run_b200(args):
         "roofline": {"kernel": "invert (assemble + factor + solve, fused)", "bound": "hbm",
                      "achieved": inv_gbs, "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                     "unit": "GB/s", "frac": inv_gbs / peak, "traffic": None,
+                     "unit": "GB/s", "frac": inv_gbs / peak, "traffic": tr("invert_blocked"),
+                     "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch)",
                      "ms_per_launch": inv_ms, "algorithmic_bytes_per_launch": inv_bytes,
                      "fp64_gflops_upper": lu_flop * wl.nactive / (inv_ms * 1e-3) / 1e9},
         "kernels": {"accumulate": {"ms": acc_ms, "GB/s": acc_gbs, "frac": acc_gbs / peak,
-                                   "algorithmic_bytes": acc_bytes},
+                                   "algorithmic_bytes": acc_bytes, "traffic": tr("accumulate")},
                     "invert": {"ms": inv_ms, "GB/s": inv_gbs, "frac": inv_gbs / peak}},
     })
     if not args.no_cpu and world == 1:

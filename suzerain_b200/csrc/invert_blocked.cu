@@ -266,7 +266,8 @@ invert_blocked_kernel(const BlockedArgs A)
     const int tid = threadIdx.x;
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT;
     constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5;
-    cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * (size_t) N * KL;
+    const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
+    cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
 
     for (int t = tid; t < MAXTERMS; t += W::NTH) S.tref[t] = K.terms->ref[t];
     for (int t = tid; t <= NBLOCK; t += W::NTH) S.tblk[t] = K.terms->blk_begin[t];
@@ -286,15 +287,17 @@ invert_blocked_kernel(const BlockedArgs A)
             if (buf == 0) bar_sync_n<BAR_FULL0>(W::NTH); else bar_sync_n<BAR_FULL1>(W::NTH);
             cplx *x = S.v + (size_t) buf * N;
             const unsigned char *jpv = S.ipiv + (size_t) buf * N;
-            const cplx *Lg = lwork + (size_t) buf * N * KL;
+            const cplx *Lg = lwork + (size_t) buf * lstride;
             const int info = S.misc[buf];
             if (info == 0) {
                 // multipliers stream in through a ring of TMA bulk copies, last columns first
                 constexpr int CH = W::CH, NB = W::NB;
+                // chunk c covers columns [CH (nchunk-1-c), +CH): aligned so that a consumed chunk is a
+                // whole number of 128-byte lines
                 const int ncols = N - 1, nchunk = (ncols + CH - 1) / CH;
                 asm volatile("fence.proxy.async;" ::: "memory");
                 auto issue = [&](int c) {
-                    const int jhi = N - 2 - c * CH, jlo = max(jhi - CH + 1, 0);
+                    const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
                     const unsigned bytes = (unsigned) ((jhi - jlo + 1) * KL * sizeof(cplx));
                     const unsigned slot = (chunk_base + c) % NB;
                     mbar_expect_tx(S.mbar + slot, bytes);
@@ -305,7 +308,7 @@ invert_blocked_kernel(const BlockedArgs A)
                 for (int c = 0; c < nchunk; ++c) {
                     const unsigned g = chunk_base + c, slot = g % NB, parity = (g / NB) & 1;
                     mbar_wait(S.mbar + slot, parity);
-                    const int jhi = N - 2 - c * CH, jlo = max(jhi - CH + 1, 0);
+                    const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
                     const cplx *Lc = S.lring + (size_t) slot * CH * KL;
                     for (int j = jhi; j >= jlo; --j) {
                         const int lm = min(KL, N - 1 - j);
@@ -324,6 +327,14 @@ invert_blocked_kernel(const BlockedArgs A)
                             x[j] = v;
                         }
                         __syncwarp();
+                    }
+                    // The multipliers of these columns are dead now: drop their (dirty) L2 lines
+                    // instead of letting them be written back to HBM.
+                    if ((CH * KL * sizeof(cplx)) % 128 == 0 && jhi - jlo + 1 == CH) {
+                        const char *g0 = reinterpret_cast<const char *>(Lg + (size_t) jlo * KL);
+                        if ((reinterpret_cast<size_t>(g0) & 127) == 0)
+                        for (int ln = lane; ln < (int) (CH * KL * sizeof(cplx) / 128); ln += 32)
+                            asm volatile("discard.global.L2 [%0], 128;" :: "l"(g0 + (size_t) ln * 128) : "memory");
                     }
                     if (lane == 0 && c + NB < nchunk) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -360,7 +371,7 @@ invert_blocked_kernel(const BlockedArgs A)
         if (q >= 2) { if (buf == 0) bar_sync_n<BAR_EMPTY0>(W::NTH); else bar_sync_n<BAR_EMPTY1>(W::NTH); }
         cplx *sv = S.v + (size_t) buf * N;
         unsigned char *jpv = S.ipiv + (size_t) buf * N;
-        cplx *Lg = lwork + (size_t) buf * N * KL;
+        cplx *Lg = lwork + (size_t) buf * lstride;
         const double km = K.km[p], kn = K.kn[p];
 
         // b = P state with the wall rows zeroed (bsmbsm_solver.hpp:150-156,
@@ -574,7 +585,7 @@ int launch_blocked(const szb_imexop *op, BlockedArgs &A, int npencil, cudaStream
     if (per_sm < 1) return 1;
     int slots = op->sm_count * per_sm;
     if (slots > npencil) slots = npencil;
-    const size_t need = (size_t) slots * 2 * N * W::KL * sizeof(cplx);
+    const size_t need = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
     if (need > op->work_bytes) {
         if (op->d_work) SZB_CUDA_OK(cudaFree(op->d_work));
         op->d_work = nullptr; op->work_bytes = 0;

@@ -364,3 +364,68 @@ def test_hundred_substeps_track_the_oracle(dev, tiny):
     torch.cuda.synchronize()
     assert int(info.abs().max()) == 0
     assert pc.relmax(a.cpu().numpy().reshape(len(tiny.km), -1), ha) <= 1e-9
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json's full sizes: oracle on a handful of pencils, size-independent
+# properties on everything
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("config,npen", [("channel_1536x384x1152", 6), ("bl_1024x256x512", 6)])
+def test_large_ny_matches_oracle(dev, config, npen):
+    """N = 1920 (Ny = 384) and N = 1280 with NRBC (Ny = 256): few pencils, full wall-normal size."""
+    case = pc.make_case(config, max_pencils=npen)
+    for solver in ("zgbsv", "zcgbsvx"):
+        got = pc.gpu_invert(case, solver, dev)
+        want = pc.oracle_invert(case, solver, nthreads=6)
+        assert want["info"] == 0 and np.all(got["info"] == 0)
+        assert np.array_equal(got["ipiv"], want["ipiv"])
+        assert pc.relmax(got["x"], want["x"]) <= TOL
+    assert pc.relmax(pc.gpu_accumulate(case, dev), pc.oracle_accumulate(case)) <= TOL
+
+
+def test_full_grid_properties(dev):
+    """Whole wave space of the 192x96x192 channel (18 336 active pencils) through the
+    device-resident operator: (i) info == 0 everywhere, (ii) dealiased pencils zero-filled,
+    (iii) linearity of the solve, (iv) accumulate o invert = identity off the wall rows,
+    (v) a strided sample of pencils against the oracle."""
+    import torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import synth
+    Nx, Ny, Nz, k, htdelta, _ = synth.CONFIGS["channel_192x96x192"]
+    case = pc.make_case("channel_192x96x192", max_pencils=4)           # operators / profiles / phi
+    op = pc.make_imexop(case)
+    g = sz.wavegrid(Nx, Nz, synth.LX, synth.LZ)
+    H = sz.OperatorHybridIsothermalDevice(op, g, sz.SolverSpec("zgbsv"), dev)
+    assert H.nactive == 96 * 191 and H.npencil == 145 * 288
+    rng = np.random.default_rng(17)
+    shape = (H.npencil, 5, Ny)
+    x = torch.from_numpy(rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).to(dev)
+    y = torch.from_numpy(rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).to(dev)
+    a, b = 0.7 - 0.2j, -1.3 + 0.4j
+    phi = case.phi
+    sx, sy, sc = x.clone(), y.clone(), (a * x + b * y)
+    ipiv = torch.zeros((H.nactive, 5 * Ny), dtype=torch.int32, device=dev)
+    H.invert_mass_plus_scaled_operator(phi, sx, ipiv=ipiv)
+    assert int(H.info.abs().max()) == 0
+    H.invert_mass_plus_scaled_operator(phi, sy)
+    H.invert_mass_plus_scaled_operator(phi, sc)
+    torch.cuda.synchronize()
+    inact = torch.from_numpy(H.h_inactive.astype(np.int64)).to(dev)
+    act = torch.from_numpy(H.h_active.astype(np.int64)).to(dev)
+    assert float(sx[inact].abs().max()) == 0.0                           # (ii)
+    lin = (sc[act] - (a * sx[act] + b * sy[act])).abs().max() / sc[act].abs().max()
+    assert float(lin) <= 1e-12                                           # (iii)
+    back = torch.zeros_like(x)
+    H.op.accumulate_batch(phi, H.km, H.kn, sx, 0.0, back, index=H.active)
+    torch.cuda.synchronize()
+    d = (back[act] - x[act]).abs()
+    scale = float(x.abs().max())
+    assert float(d[:, :, 1:-1].max()) / scale <= 1e-11                   # (iv) interior points
+    assert float(d[:, 4, :].max()) / scale <= 1e-11                      #      and the continuity rows at the walls
+    sel = np.linspace(0, H.nactive - 1, 24).astype(int)                 # (v)
+    P = pc.oracle_problem(case)
+    hx = x.cpu().numpy().reshape(H.npencil, -1)[H.h_active[sel]]
+    want = P.invert("zgbsv", phi, H.h_km[sel], H.h_kn[sel], hx, want_ipiv=True, nthreads=8)
+    got = sx.cpu().numpy().reshape(H.npencil, -1)[H.h_active[sel]]
+    assert pc.relmax(got, want["x"]) <= TOL
+    assert np.array_equal(ipiv.cpu().numpy()[sel], want["ipiv"])
