@@ -230,7 +230,7 @@ def run_reference(args):
                  "e2e": {"value": ns, "unit": "ns/gridpoint/substep", "h2d_bytes_per_step": 0,
                          "d2h_bytes_per_step": 0},
                  "gpu_launches": 0, "dtype": "f64"})
-    print(json.dumps(line), flush=True)
+    print_line(line)
 
 
 def base_line(args, wl):
@@ -406,13 +406,21 @@ def run_b200(args):
         t, sample, kind = cpu_substep_time(wl, args.solver, cores, args.cpu_seconds)
         line["cpu_baseline"] = {"value": t * 1e9 / wl.gridpoints, "unit": "ns/gridpoint/substep",
                                 "cores": cores, "kind": kind, "sample": sample}
-    print(json.dumps(line), flush=True)
+    print_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # Libraries (NCCL's version banner, OpenMP notices) write to stdout; the contract is ONE
+    # JSON line there.  Route fd 1 to stderr for the duration and print the line to the real one.
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    global print_line
+    print_line = lambda obj: (out.write(json.dumps(obj) + "\n"), out.flush())
     if args.impl == "reference":
         run_reference(args)
     else:
