@@ -95,7 +95,7 @@ struct BlkCfg {
     static constexpr int RPG = RPG_;                // rows per trailing-update task
     static constexpr int NG = (NS + RPG_ - 1) / RPG_;
     static constexpr int NCOEF = 75;
-    static constexpr int CH = 8, NB = 2;            // solver: L columns per TMA chunk, ring depth
+    static constexpr int CH = 4, NB = 3;            // solver: L columns per TMA chunk, ring depth
     static_assert(RW % P == 0, "window rows come in groups of five");
     static_assert(NS <= 64, "panel warp holds two row slots per lane");
     static_assert((CR & (CR - 1)) == 0, "ring size must be a power of two");
@@ -114,6 +114,7 @@ struct Smem {
     cplx *win;        // [NS][CW]        the window
     cplx *lp;         // [NS][P]         panel multipliers by slot (zeros past a pivot row's own step)
     cplx *lcol;       // [P][KL]         the same multipliers in zgbtf2 (column, row offset) order
+    cplx *xch;        // [2][2][1 + P]   per column parity, per panel warp: {key, label, slot}, candidate row
     cplx *stage;      // [2][P][CW]      assembled rows waiting to enter
     cplx *coef;       // [CR][75]        per-point block coefficients
     cplx *alpha;      // [MAXTERMS]
@@ -131,7 +132,7 @@ struct Smem {
 template <class W>
 __host__ __device__ inline size_t blocked_smem_bytes(int N)
 {
-    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + W::NS * P + P * W::KL + 2 * P * W::CW + W::CR * W::NCOEF
+    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + W::NS * P + P * W::KL + 4 * (1 + P) + 2 * P * W::CW + W::CR * W::NCOEF
                                + MAXTERMS + 2 * (size_t) N + W::NB * W::CH * W::KL);
     b += 8 * W::NB + 4 * (2 * P + 6) + 2 * 64 + 2 * (size_t) N + MAXTERMS + 80;
     return (b + 15) & ~(size_t) 15;
@@ -145,6 +146,7 @@ __device__ __forceinline__ Smem<W> carve(unsigned char *raw, int N)
     S.win = p;   p += W::NS * W::CW;
     S.lp = p;    p += W::NS * P;
     S.lcol = p;  p += P * W::KL;
+    S.xch = p;   p += 4 * (1 + P);
     S.stage = p; p += 2 * P * W::CW;
     S.coef = p;  p += W::CR * W::NCOEF;
     S.alpha = p; p += MAXTERMS;
@@ -265,7 +267,7 @@ invert_blocked_kernel(const BlockedArgs A)
     const Smem<W> S = carve<W>(smem_raw, N);
     const int tid = threadIdx.x;
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT;
-    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5;
+    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_PANEL = 6;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
 
@@ -400,105 +402,100 @@ invert_blocked_kernel(const BlockedArgs A)
         for (int c = tid; c < CW; c += NT) S.win[(size_t) RW * CW + c] = c < N ? sv[c] : cplx(0.0, 0.0);
         bar_sync_n<BAR_ALL>(NT);
 
-        // panel-warp state: the logical rows held by this lane's two slots
-        int lg0 = lane < RW ? lane : INT_MIN, lg1 = lane + 32 < RW ? lane + 32 : INT_MIN;
-        const bool rhs0 = lane == RW, rhs1 = lane + 32 == RW;
-        const bool have0 = lane < NS, have1 = lane + 32 < NS;
-        int pk0 = P, pk1 = P;           // panel step at which the slot's row became a pivot row
+        // panel-warp state (warps 0 and 1 factor the panels together): the logical row held by
+        // this lane's row slot
+        const int fslot = lane + 32 * warp;                  // meaningful for warp < 2
+        const bool have = warp < 2 && fslot < NS, rhs = fslot == RW, liveb = have && !rhs;
+        int lg = (warp < 2 && fslot < RW) ? fslot : INT_MIN;
+        int pk = P;                     // panel step at which the slot's row became a pivot row
         int ju = 0, info = 0, par = 0;
         int jc = 0;                     // j mod CW
 
         for (int j = 0; j < N; j += P, par ^= 1) {
             int *pivslot = S.pivslot + par * P;
             unsigned char *isp = S.isp + par * 64;
-            if (warp == 0) {
+            if (warp < 2) {
                 // ---------------- phase 1a: factor the panel in registers ----------------
+                // One row slot per lane, two warps; per column the warps exchange their best
+                // candidate (key, label, slot, row) through shared memory and one 64-thread
+                // barrier.
                 const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;     // rows that entered after the previous panel
-                cplx a0[P], a1[P];
+                cplx a[P];
 #pragma unroll
                 for (int m = 0; m < P; ++m) {
                     int cs = jc + m; if (cs >= CW) cs -= CW;
-                    a0[m] = cplx(0.0, 0.0); a1[m] = cplx(0.0, 0.0);
-                    if (have0) a0[m] = pk0 < P ? stg[pk0 * CW + cs] : S.win[(size_t) lane * CW + cs];
-                    if (have1) a1[m] = pk1 < P ? stg[pk1 * CW + cs] : S.win[(size_t) (lane + 32) * CW + cs];
+                    a[m] = cplx(0.0, 0.0);
+                    if (have) a[m] = pk < P ? stg[pk * CW + cs] : S.win[(size_t) fslot * CW + cs];
                 }
-                // rows that retired in the previous panel were replaced by rows j+RW-P+k
-                if (pk0 < P) { lg0 = j + RW - P + pk0; pk0 = P; }
-                if (pk1 < P) { lg1 = j + RW - P + pk1; pk1 = P; }
-                const bool live0b = have0 && !rhs0, live1b = have1 && !rhs1;
+                // a row that retired in the previous panel was replaced by row j+RW-P+k
+                if (pk < P) { lg = j + RW - P + pk; pk = P; }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
                     const int col = j + k, hi = min(col + KL, N - 1);
-                    // izamax over rows col..hi: compare the top 32 bits first; only a near
-                    // tie needs the low word and the smallest-row rule
-                    const bool c0 = live0b && pk0 == P && lg0 <= hi;
-                    const bool c1 = live1b && pk1 == P && lg1 <= hi;
-                    const long long k0 = c0 ? __double_as_longlong(cabs1(a0[k])) : -1ll;
-                    const long long k1 = c1 ? __double_as_longlong(cabs1(a1[k])) : -1ll;
-                    bool second = k1 > k0 || (k1 == k0 && c1 && lg1 < lg0);
-                    const long long kb = second ? k1 : k0;
-                    const int lb = second ? lg1 : lg0;
-                    const int hi32 = (int) (kb >> 32);
+                    // izamax over rows col..hi: compare the top 32 bits first; only a near tie
+                    // needs the low word and the smallest-row rule
+                    const bool cnd = liveb && pk == P && lg <= hi;
+                    const long long key = cnd ? __double_as_longlong(cabs1(a[k])) : -1ll;
+                    const int hi32 = (int) (key >> 32);
                     const int mh = __reduce_max_sync(0xffffffffu, hi32);
-                    bool iswin = hi32 == mh && kb >= 0;
+                    bool iswin = hi32 == mh && key >= 0;
                     unsigned bal = __ballot_sync(0xffffffffu, iswin);
                     if (bal & (bal - 1)) {                         // several lanes share the top word
-                        const unsigned lo32 = (unsigned) (kb & 0xffffffffll);
+                        const unsigned lo32 = (unsigned) (key & 0xffffffffll);
                         const unsigned ml = __reduce_max_sync(0xffffffffu, iswin ? lo32 : 0u);
                         iswin = iswin && lo32 == ml;
-                        const int lmin = __reduce_min_sync(0xffffffffu, iswin ? lb : INT_MAX);
-                        iswin = iswin && lb == lmin;
+                        const int lmin = __reduce_min_sync(0xffffffffu, iswin ? lg : INT_MAX);
+                        iswin = iswin && lg == lmin;
                         bal = __ballot_sync(0xffffffffu, iswin);
                     }
-                    const int wlane = __ffs(bal) - 1;
-                    const int lwin = __shfl_sync(0xffffffffu, lb, wlane);
+                    cplx *rec = S.xch + ((k & 1) * 2 + warp) * (1 + P);
+                    if (bal == 0) {
+                        if (lane == 0) *reinterpret_cast<long long *>(rec) = -1ll;
+                    } else if (iswin) {
+                        *reinterpret_cast<long long *>(rec) = key;
+                        reinterpret_cast<int *>(rec)[2] = lg;
+                        reinterpret_cast<int *>(rec)[3] = fslot;
+#pragma unroll
+                        for (int m = k; m < P; ++m) rec[1 + m] = a[m];
+                    }
+                    bar_sync_n<BAR_PANEL>(64);
+                    const cplx *r0 = S.xch + ((k & 1) * 2 + 0) * (1 + P), *r1 = r0 + (1 + P);
+                    const long long k0 = *reinterpret_cast<const long long *>(r0);
+                    const long long k1 = *reinterpret_cast<const long long *>(r1);
+                    const int l0 = reinterpret_cast<const int *>(r0)[2], l1 = reinterpret_cast<const int *>(r1)[2];
+                    const bool second = k1 > k0 || (k1 == k0 && k1 >= 0 && l1 < l0);
+                    const cplx *rw = second ? r1 : r0;
+                    const int lwin = second ? l1 : l0;
+                    const int wslot = reinterpret_cast<const int *>(rw)[3];
                     const int jp = lwin - col;
                     cplx pv[P];
 #pragma unroll
-                    for (int m = k; m < P; ++m) {
-                        const cplx mine = second ? a1[m] : a0[m];
-                        pv[m].x = __shfl_sync(0xffffffffu, mine.x, wlane);
-                        pv[m].y = __shfl_sync(0xffffffffu, mine.y, wlane);
-                    }
+                    for (int m = k; m < P; ++m) pv[m] = rw[1 + m];
                     // interchange = relabel: the slot holding row `col` takes the winner's label
-                    if (live0b && pk0 == P && lg0 == col) lg0 = lwin;
-                    if (live1b && pk1 == P && lg1 == col) lg1 = lwin;
-                    if (iswin) {
-                        if (second) { pk1 = k; lg1 = col; pivslot[k] = lane + 32; }
-                        else        { pk0 = k; lg0 = col; pivslot[k] = lane; }
-                    }
-                    if (lane == 0) jpv[col] = (unsigned char) jp;
-                    if (is_zero(pv[k])) { info = col + 1; break; }
+                    if (liveb && pk == P && lg == col) lg = lwin;
+                    if (have && fslot == wslot) { pk = k; lg = col; pivslot[k] = fslot; }
+                    if (tid == 0) jpv[col] = (unsigned char) jp;
+                    if ((second ? k1 : k0) == 0) { info = col + 1; break; }      // |re|+|im| == 0: zero pivot
                     ju = max(ju, min(col + KU + jp, N - 1));
                     const cplx rinv = recip_fast(pv[k]);
-                    cplx *lc = S.lcol + k * KL - (col + 1);           // lc[row] = L(row, col)
-                    if (have0 && pk0 == P) {
-                        const cplx l = a0[k] * rinv; a0[k] = l;
+                    if (have && pk == P) {
+                        const cplx l = a[k] * rinv; a[k] = l;
 #pragma unroll
-                        for (int m = k + 1; m < P; ++m) submul(a0[m], l, pv[m]);
-                        if (rhs0) sv[col] = l;
-                        else if (lg0 <= hi) lc[lg0] = l;
-                    }
-                    if (have1 && pk1 == P) {
-                        const cplx l = a1[k] * rinv; a1[k] = l;
-#pragma unroll
-                        for (int m = k + 1; m < P; ++m) submul(a1[m], l, pv[m]);
-                        if (rhs1) sv[col] = l;
-                        else if (lg1 <= hi) lc[lg1] = l;
+                        for (int m = k + 1; m < P; ++m) submul(a[m], l, pv[m]);
+                        if (rhs) sv[col] = l;
+                        else if (lg <= hi) S.lcol[k * KL + lg - (col + 1)] = l;      // L(lg, col)
                     }
                 }
                 // multipliers by slot; a pivot row keeps only the part below its own diagonal
+                if (have) {
 #pragma unroll
-                for (int m = 0; m < P; ++m) {
-                    if (have0) S.lp[lane * P + m] = m < pk0 ? a0[m] : cplx(0.0, 0.0);
-                    if (have1) S.lp[(lane + 32) * P + m] = m < pk1 ? a1[m] : cplx(0.0, 0.0);
+                    for (int m = 0; m < P; ++m) S.lp[fslot * P + m] = m < pk ? a[m] : cplx(0.0, 0.0);
+                    isp[fslot] = pk < P;
                 }
-                if (have0) isp[lane] = pk0 < P;
-                if (have1) isp[lane + 32] = pk1 < P;
-                if (lane == 0) { S.misc[2] = ju; S.misc[3] = info; }
+                if (tid == 0) { S.misc[2] = ju; S.misc[3] = info; }
             } else {
                 // -------- phase 1b: refresh after the previous panel, assemble the next rows --------
-                const int t0 = tid - 32, nt = NT - 32;
+                const int t0 = tid - 64, nt = NT - 64;
                 if (j > 0) {
                     const int jo = j - P;                         // previous panel
                     const int *opiv = S.pivslot + (par ^ 1) * P;
