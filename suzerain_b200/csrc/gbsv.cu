@@ -460,16 +460,21 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     if (!d_info) return -14;
     if (npencil == 0) return 0;
 
-    // zgbsv with a single right hand side per pencil: the blocked shared-memory-window
-    // kernel (invert_blocked.cu).  SZB_INVERT=v1 / v2 in the environment selects the
-    // generic global-memory kernel / the register-window kernel (invert_window.cu).
+    // zgbsv with a single right hand side per pencil: the pipelined blocked
+    // shared-memory-window kernel (invert_pipe.cu).  SZB_INVERT=v1 / v2 / v3 in the
+    // environment selects the generic global-memory kernel / the register-window kernel
+    // (invert_window.cu) / the unpipelined blocked kernel (invert_blocked.cu).
     if (spec->method == SZB_SOLVER_ZGBSV && nextra == 0) {
         static const int which = [] {
             const char *e = std::getenv("SZB_INVERT");
-            return (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') ? e[1] - '0' : 3;
+            return (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '4') ? e[1] - '0' : 4;
         }();
         int rc = 1;
-        if (which == 3)
+        if (which == 4)
+            rc = invert_pipe_dispatch(op, phi, npencil, d_km, d_kn, d_index,
+                                      reinterpret_cast<cplx *>(d_state), field_stride,
+                                      pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
+        if (which == 3 || (which == 4 && rc == 1))
             rc = invert_blocked_dispatch(op, phi, npencil, d_km, d_kn, d_index,
                                          reinterpret_cast<cplx *>(d_state), field_stride,
                                          pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);

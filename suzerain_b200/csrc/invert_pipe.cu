@@ -1,0 +1,612 @@
+// invert_pipe.cu -- batched invert of (M + phi L), version 4: the blocked banded LU of
+// invert_blocked.cu with the panel factorisation taken off the critical path of the
+// trailing update (two-stage software pipeline per panel).
+//
+// Replaces the hot loop of invert_mass_plus_scaled_operator
+// (apps/perfect/operator_hybrid_isothermal.cpp:617-686) for the zgbsv solver
+// specification: suzerain_rholut_imexop_packf (rholut_imexop.def:41-597) +
+// IsothermalPATPTEnforcer::op/rhs (:470-525) + bsmbsm_solver::supply_B /
+// zgbtrf + zgbtrs('T') / demand_X (bsmbsm_solver.cpp:155-182).  One persistent CTA per
+// pencil slot; the matrix is assembled, factored and consumed on the SM and never
+// touches HBM.
+//
+// Window, slot indirection, right-hand side row and solver warp are those of v3.  What
+// changes is the schedule.  With j = 5 t the first column of panel t, one iteration is
+//
+//   panel warp   : L(t-1)  block t (columns j..j+4) of every row -= panel t-1's rank-5
+//                          update, in registers (two row slots per lane); rows that
+//                          entered after panel t-1 come straight from the stage
+//                  F(t)    factor panel t in registers: per column one REDUX pivot
+//                          search, the winner's row and its speculatively computed
+//                          reciprocal broadcast by shuffles; multipliers to the scratch
+//   update warps : U(t-1)  rank-5 update of columns j+5..ju(t-1) of the window
+//                  R(t-1)  the rows entering after panel t-1 replace the retired pivot
+//                          rows (all column slots but block t's), recycled column slots
+//                          are zeroed
+//                  A(t)    assemble the five rows entering after panel t into the stage
+//   one CTA barrier
+//
+// so the serial chain per panel is L + F only; tools/pipelined_window_model.py is an
+// executable model of the schedule that checks the two sides for shared-memory races.
+//
+// Arithmetic per element is the same sequence of FMAs as the unblocked zgbtf2 sweep;
+// the pivot rule is izamax's (first maximum of |re|+|im|), so ipiv is LAPACK's.
+#include <climits>
+#include <cstdio>
+
+#include "invert_common.cuh"
+
+namespace szb {
+
+namespace {
+
+using namespace fused;
+
+template <int KL_, int KU_, int CR_, int NWU_, int RPG_, int MINB_>
+struct PipeCfg {
+    static constexpr int MINB = MINB_;              // CTAs per SM the register budget is sized for
+    static constexpr int KL = KL_, KU = KU_, KV = KL_ + KU_;
+    static constexpr int RW = KL_ + P + 1;          // matrix row slots (one spare row keeps blocks aligned)
+    static constexpr int NS = RW + 1;               // + the right-hand-side row (slot RW)
+    static constexpr int NQ = NS > 32 ? 2 : 1;      // row slots per panel-warp lane
+    static constexpr int CW = KV + P + 1;           // column slots
+    static constexpr int CR = CR_;                  // coefficient ring (collocation points), power of 2
+    static constexpr int NWU = NWU_;                // update warps; warp NWU factors the panels
+    static constexpr int NTU = 32 * NWU_, NT = NTU + 32, NTH = NT + 32;
+    static constexpr int RPG = RPG_;                // rows per trailing-update task
+    static constexpr int NG = (NS + RPG_ - 1) / RPG_;
+    static constexpr int NCOEF = 75;
+    static constexpr int CH = 4, NB = 3;            // solver: L columns per TMA chunk, ring depth
+    static_assert(RW % P == 0, "window rows come in groups of five");
+    static_assert(NS <= 64, "panel warp holds two row slots per lane");
+    static_assert((CR & (CR - 1)) == 0, "ring size must be a power of two");
+};
+
+struct PipeArgs {
+    PackArgs pk;
+    int npencil; const int *index;
+    cplx *state; size_t fs, ps;
+    int *ipiv_out, *info_out, *iters_out;
+    cplx *lwork;            // per CTA: 2 buffers of N*KL multipliers
+};
+
+template <class W>
+struct PSmem {
+    cplx *win;        // [NS][CW]        the window
+    cplx *lp;         // [2][NS][P]      per panel parity: multipliers by slot (zeros past a pivot row's own step)
+    cplx *ufx;        // [P][P]          panel warp: fixed-up pivot rows of the previous panel, block t
+    cplx *stage;      // [2][P][CW]      assembled rows waiting to enter
+    cplx *coef;       // [CR][75]        per-point block coefficients
+    cplx *alpha;      // [MAXTERMS]
+    cplx *v;          // [2][N]          b -> y -> x per buffer
+    cplx *lring;      // [NB][CH*KL]     multipliers prefetched by TMA for the solver warp
+    unsigned long long *mbar;   // [NB]
+    int *pivslot;     // [2][P]
+    int *misc;        // [0..1] info per buffer, [2..3] ju per panel parity, [4..5] panel info per buffer, [6..9] retired-slot mask per panel parity
+    unsigned char *isp;    // [2][64]    slot retired by the panel of that parity
+    unsigned char *ipiv;   // [2][N]     jp per column
+    unsigned char *tref;   // [MAXTERMS]
+    unsigned char *tblk;   // [76]
+};
+
+template <class W>
+__host__ __device__ inline size_t pipe_smem_bytes(int N)
+{
+    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + 2 * W::NS * P + P * P + 2 * P * W::CW + W::CR * W::NCOEF
+                               + MAXTERMS + 2 * (size_t) N + W::NB * W::CH * W::KL);
+    b += 8 * W::NB + 4 * (2 * P + 12) + 2 * 64 + 2 * (size_t) N + MAXTERMS + 80;
+    return (b + 15) & ~(size_t) 15;
+}
+
+template <class W>
+__device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
+{
+    PSmem<W> S;
+    cplx *p = reinterpret_cast<cplx *>(raw);
+    S.win = p;   p += W::NS * W::CW;
+    S.lp = p;    p += 2 * W::NS * P;
+    S.ufx = p;   p += P * P;
+    S.stage = p; p += 2 * P * W::CW;
+    S.coef = p;  p += W::CR * W::NCOEF;
+    S.alpha = p; p += MAXTERMS;
+    S.v = p;     p += 2 * (size_t) N;
+    S.lring = p; p += W::NB * W::CH * W::KL;
+    unsigned char *q = reinterpret_cast<unsigned char *>(p);
+    S.mbar = reinterpret_cast<unsigned long long *>(q); q += 8 * W::NB;
+    S.pivslot = reinterpret_cast<int *>(q); q += 4 * 2 * P;
+    S.misc = reinterpret_cast<int *>(q); q += 4 * 12;
+    S.isp = q;  q += 2 * 64;
+    S.ipiv = q; q += 2 * (size_t) N;
+    S.tref = q; q += MAXTERMS;
+    S.tblk = q;
+    return S;
+}
+
+__device__ __forceinline__ cplx shfl_c(cplx v, int src)
+{
+    return cplx(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// predicated stores: one instruction, no divergent branch on the panel warp's chain
+__device__ __forceinline__ void st_global_if(cplx *p, cplx v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}"
+                 :: "l"(p), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
+}
+__device__ __forceinline__ void st_shared_if(cplx *p, cplx v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}"
+                 :: "r"(smem_u32(p)), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
+}
+
+// The rare exact pivot decision (near ties on the top word, two candidates in one lane,
+// tiny or huge magnitudes, zero pivots): izamax's first maximum of the full 64-bit
+// |re|+|im| with the smallest logical row breaking ties.  Returns
+// src | wq << 8 | zero-pivot << 16 | (this lane's own better slot) << 24.
+__device__ __noinline__ int exact_pivot(long long key0, long long key1, int lg0, int lg1)
+{
+    const bool sq = key1 > key0 || (key1 == key0 && key0 >= 0 && lg1 < lg0);
+    const long long kb = sq ? key1 : key0;
+    const int lgb = sq ? lg1 : lg0;
+    const int hi32 = (int) (kb >> 32);
+    const int mh = __reduce_max_sync(0xffffffffu, hi32);
+    bool iswin = hi32 == mh && kb >= 0;
+    const unsigned lo32 = (unsigned) (kb & 0xffffffffll);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, iswin ? lo32 : 0u);
+    iswin = iswin && lo32 == ml;
+    const int lmin = __reduce_min_sync(0xffffffffu, iswin ? lgb : INT_MAX);
+    iswin = iswin && lgb == lmin;
+    const unsigned bal = __ballot_sync(0xffffffffu, iswin);
+    const int src = bal ? __ffs(bal) - 1 : 0;
+    const int wq = __shfl_sync(0xffffffffu, (int) sq, src);
+    const int zp = bal == 0 || __shfl_sync(0xffffffffu, (int) (kb == 0), src) != 0;
+    return src | wq << 8 | zp << 16 | (int) sq << 24;
+}
+// ... and a reciprocal that cannot overflow prematurely
+__device__ __noinline__ double2 exact_recip(double x, double y)
+{
+    const cplx r = recip_fast(cplx(x, y));
+    return make_double2(r.x, r.y);
+}
+
+template <class W>
+__global__ void __launch_bounds__(W::NTH, W::MINB)
+invert_pipe_kernel(const PipeArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const PackArgs &K = A.pk;
+    const int N = K.N, n = K.n;
+    const PSmem<W> S = pipe_carve<W>(smem_raw, N);
+    const int tid = threadIdx.x;
+    constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
+    constexpr int NQ = W::NQ;
+    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_LOOK = 7;
+    const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
+    cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
+
+    for (int t = tid; t < MAXTERMS; t += W::NTH) S.tref[t] = K.terms->ref[t];
+    for (int t = tid; t <= NBLOCK; t += W::NTH) S.tblk[t] = K.terms->blk_begin[t];
+    if (tid == NT) {
+        for (int b = 0; b < W::NB; ++b) mbar_init(S.mbar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= NT) {
+        // =================== solver warp: L^T back substitution ===================
+        const int lane = tid - NT;
+        int q = 0;
+        unsigned chunk_base = 0;        // running chunk count: ring slot and mbarrier phase
+        for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
+            const int buf = q & 1;
+            if (buf == 0) bar_sync_n<BAR_FULL0>(W::NTH); else bar_sync_n<BAR_FULL1>(W::NTH);
+            cplx *x = S.v + (size_t) buf * N;
+            const unsigned char *jpv = S.ipiv + (size_t) buf * N;
+            const cplx *Lg = lwork + (size_t) buf * lstride;
+            const int info = S.misc[buf];
+            if (info == 0) {
+                // multipliers stream in through a ring of TMA bulk copies, last columns first
+                constexpr int CH = W::CH, NB = W::NB;
+                // chunk c covers columns [CH (nchunk-1-c), +CH): aligned so that a consumed chunk is a
+                // whole number of 128-byte lines
+                const int ncols = N - 1, nchunk = (ncols + CH - 1) / CH;
+                asm volatile("fence.proxy.async;" ::: "memory");
+                auto issue = [&](int c) {
+                    const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
+                    const unsigned bytes = (unsigned) ((jhi - jlo + 1) * KL * sizeof(cplx));
+                    const unsigned slot = (chunk_base + c) % NB;
+                    mbar_expect_tx(S.mbar + slot, bytes);
+                    tma_bulk_g2s(S.lring + (size_t) slot * CH * KL, Lg + (size_t) jlo * KL, bytes,
+                                 S.mbar + slot);
+                };
+                if (lane == 0) for (int c = 0; c < min(NB, nchunk); ++c) issue(c);
+                for (int c = 0; c < nchunk; ++c) {
+                    const unsigned g = chunk_base + c, slot = g % NB, parity = (g / NB) & 1;
+                    mbar_wait(S.mbar + slot, parity);
+                    const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
+                    const cplx *Lc = S.lring + (size_t) slot * CH * KL;
+                    for (int j = jhi; j >= jlo; --j) {
+                        const int lm = min(KL, N - 1 - j);
+                        const cplx *Lj = Lc + (size_t) (j - jlo) * KL;
+                        cplx s(0.0, 0.0);
+                        for (int i = 1 + lane; i <= lm; i += 32) addmul(s, Lj[i - 1], x[j + i]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+                            s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+                        }
+                        if (lane == 0) {
+                            cplx v = x[j] - s;
+                            const int l = j + jpv[j];
+                            if (l != j) { const cplx t = x[l]; x[l] = v; v = t; }
+                            x[j] = v;
+                        }
+                        __syncwarp();
+                    }
+                    // The multipliers of these columns are dead now: drop their (dirty) L2 lines
+                    // instead of letting them be written back to HBM.
+                    if ((CH * KL * sizeof(cplx)) % 128 == 0 && jhi - jlo + 1 == CH) {
+                        const char *g0 = reinterpret_cast<const char *>(Lg + (size_t) jlo * KL);
+                        if ((reinterpret_cast<size_t>(g0) & 127) == 0)
+                        for (int ln = lane; ln < (int) (CH * KL * sizeof(cplx) / 128); ln += 32)
+                            asm volatile("discard.global.L2 [%0], 128;" :: "l"(g0 + (size_t) ln * 128) : "memory");
+                    }
+                    if (lane == 0 && c + NB < nchunk) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(c + NB);
+                    }
+                }
+                chunk_base += nchunk;
+                // state = P^T x (bsmbsm_solver.hpp:274-280)
+                cplx *v = A.state + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
+                for (int e = lane; e < N; e += 32) {
+                    const int f = e / n, y = e - f * n;
+                    v[(size_t) f * A.fs + y] = x[5 * y + f];
+                }
+            }
+            if (lane == 0) {
+                A.info_out[p] = info;
+                if (A.iters_out) A.iters_out[p] = 0;
+            }
+            if (A.ipiv_out)
+                for (int k = lane; k < N; k += 32) A.ipiv_out[(size_t) p * N + k] = k + jpv[k] + 1;
+            __threadfence_block();
+            if (p + 2 * (int) gridDim.x < A.npencil) {
+                if (buf == 0) bar_arrive_n<BAR_EMPTY0>(W::NTH); else bar_arrive_n<BAR_EMPTY1>(W::NTH);
+            }
+        }
+        return;
+    }
+
+    // ============================ compute warps ============================
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool panel = warp == W::NWU;
+    int q = 0;
+    for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
+        const int buf = q & 1;
+        if (q >= 2) { if (buf == 0) bar_sync_n<BAR_EMPTY0>(W::NTH); else bar_sync_n<BAR_EMPTY1>(W::NTH); }
+        cplx *sv = S.v + (size_t) buf * N;
+        unsigned char *jpv = S.ipiv + (size_t) buf * N;
+        cplx *Lg = lwork + (size_t) buf * lstride;
+        const double km = K.km[p], kn = K.kn[p];
+
+        // b = P state with the wall rows zeroed (bsmbsm_solver.hpp:150-156,
+        // operator_hybrid_isothermal.cpp:516-525)
+        {
+            const cplx *v = A.state + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
+            for (int e = tid; e < N; e += NT) {
+                const int f = e / n, y = e - f * n;
+                cplx val = v[(size_t) f * A.fs + y];
+                if (K.with_bc && f < 4
+                    && ((y == 0 && K.wall_begin == 0) || (y == n - 1 && K.wall_end == 2)))
+                    val = cplx(0.0, 0.0);
+                sv[5 * y + f] = val;
+            }
+        }
+        for (int t = tid; t < K.terms->nterms; t += NT)
+            S.alpha[t] = wave_factor(K.terms->wave[t], km, kn) * K.terms->sc[t];
+        if (tid == 0) { S.misc[buf] = 0; S.misc[4 + buf] = 0; }
+        if (tid < 2 * 64) S.isp[tid] = 0;
+        bar_sync_n<BAR_ALL>(NT);
+        for (int y = 0; y <= RW / 5 + K.ku; ++y) compute_coef<W>(K, S, y, tid, NT);
+        bar_sync_n<BAR_ALL>(NT);
+        // initial window: logical rows 0..RW-1 in slots 0..RW-1; RHS row t_c = b_c
+        for (int blk = 0; blk < RW / 5; ++blk)
+            assemble_block<W>(K, S, km, kn, blk, S.win + (size_t) blk * P * CW, tid, NT);
+        for (int c = tid; c < CW; c += NT) S.win[(size_t) RW * CW + c] = c < N ? sv[c] : cplx(0.0, 0.0);
+        bar_sync_n<BAR_ALL>(NT);
+
+        int info = 0;
+        if (panel) {
+            // ====================== panel warp: F(t) ======================
+            // Row slot lane + 32 q lives in this lane.  lg: the logical row the slot holds
+            // (INT_MAX for the right-hand side and for absent slots: never a candidate);
+            // pk: P while the row is in play, 0..P-1 once it is this panel's pivot row,
+            // -1 for absent slots.  a[q][0] is the column being eliminated; finished columns
+            // are shifted out so that the column loop is one body (instruction-cache footprint).
+            int lg[NQ], pk[NQ];
+            cplx a[NQ][P];
+#pragma unroll
+            for (int qq = 0; qq < NQ; ++qq) {
+                const int slot = lane + 32 * qq;
+                lg[qq] = slot < RW ? slot : INT_MAX;
+                pk[qq] = slot < NS ? P : -1;
+            }
+            int ju = 0, jc = 0, par = 0;
+            for (int j = 0; j < N; j += P, par ^= 1) {
+                // block t of every row: entering rows from the stage, the others from the
+                // window once the update warps have applied panel t-1 to it
+                if (j > 0) bar_sync_n<BAR_LOOK>(NT);
+                {
+                    const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;
+                    int cs[P];
+#pragma unroll
+                    for (int m = 0; m < P; ++m) { cs[m] = jc + m; if (cs[m] >= CW) cs[m] -= CW; }
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq) {
+                        const bool ret = pk[qq] >= 0 && pk[qq] < P;
+                        const cplx *src = ret ? stg + pk[qq] * CW
+                                              : S.win + (size_t) (pk[qq] >= 0 ? lane + 32 * qq : 0) * CW;
+#pragma unroll
+                        for (int m = 0; m < P; ++m) a[qq][m] = src[cs[m]];
+                        // a row that retired in the previous panel was replaced by row j-P+RW+k
+                        if (ret) { lg[qq] = j - P + RW + pk[qq]; pk[qq] = P; }
+                    }
+                }
+                cplx *lpn = S.lp + (size_t) par * NS * P + lane * P;      // + 32 P q: this lane's slots
+                cplx *Lcol = Lg + (size_t) j * KL - (j + 1);                // L(lg, col) at Lcol[lg]
+#pragma unroll 1
+                for (int k = 0; k < P; ++k) {
+                    const int col = j + k, hi = min(col + KL, N - 1);
+                    // izamax over rows col..hi on the top 32 bits of |re|+|im|; anything but a
+                    // unique, comfortably scaled maximum takes the exact path
+                    int h[NQ];
+                    double mag[NQ];
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq) {
+                        mag[qq] = cabs1(a[qq][0]);
+                        h[qq] = (pk[qq] == P && lg[qq] <= hi) ? __double2hiint(mag[qq]) : -1;
+                    }
+                    const bool sq = NQ == 2 && h[NQ - 1] > h[0];
+                    const int mh = __reduce_max_sync(0xffffffffu, sq ? h[NQ - 1] : h[0]);
+                    // every lane inverts its own better candidate while the search is in flight
+                    const cplx cb = sq ? a[NQ - 1][0] : a[0][0];
+                    cplx rsp;
+                    {
+                        const double d = 1.0 / fma(cb.x, cb.x, cb.y * cb.y);
+                        rsp = cplx(cb.x * d, -cb.y * d);
+                    }
+                    const unsigned b0 = __ballot_sync(0xffffffffu, h[0] == mh);
+                    const unsigned b1 = NQ == 2 ? __ballot_sync(0xffffffffu, h[NQ - 1] == mh) : 0u;
+                    const unsigned ball = b0 | b1;
+                    int src, wq;
+                    bool zp = false;
+                    // 0x22f00000 ~ 1e-140, 0x5d000000 ~ 1e+140
+                    if (mh >= 0x22f00000 && mh <= 0x5d000000 && (b0 & b1) == 0 && (ball & (ball - 1)) == 0) {
+                        src = __ffs(ball) - 1;
+                        wq = b1 != 0;
+                    } else {
+                        const long long key0 = h[0] >= 0 ? __double_as_longlong(mag[0]) : -1ll;
+                        const long long key1 = NQ == 2 && h[NQ - 1] >= 0 ? __double_as_longlong(mag[NQ - 1]) : -1ll;
+                        const int e = exact_pivot(key0, key1, lg[0], lg[NQ - 1]);
+                        src = e & 0xff; wq = (e >> 8) & 1; zp = (e >> 16) & 1;
+                        const cplx ce = (e >> 24) ? a[NQ - 1][0] : a[0][0];
+                        const double2 r = exact_recip(ce.x, ce.y);
+                        rsp = cplx(r.x, r.y);
+                    }
+                    const cplx rinv = shfl_c(rsp, src);
+                    cplx pv[P];
+                    int lwin;
+                    if (NQ == 2 && wq) {                           // warp-uniform
+#pragma unroll
+                        for (int m = 1; m < P; ++m) pv[m] = shfl_c(a[NQ - 1][m], src);
+                        lwin = __shfl_sync(0xffffffffu, lg[NQ - 1], src);
+                    } else {
+#pragma unroll
+                        for (int m = 1; m < P; ++m) pv[m] = shfl_c(a[0][m], src);
+                        lwin = __shfl_sync(0xffffffffu, lg[0], src);
+                    }
+                    // interchange = relabel: the slot holding row `col` takes the winner's label
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq) {
+                        if (pk[qq] == P && lg[qq] == col) lg[qq] = lwin;
+                        if (lane == src && wq == qq) { pk[qq] = k; lg[qq] = col; }
+                    }
+                    if (lane == 0) {
+                        jpv[col] = (unsigned char) (lwin - col);
+                        S.pivslot[par * P + k] = src + 32 * wq;
+                    }
+                    if (zp) { info = col + 1; break; }             // |re|+|im| == 0: zero pivot
+                    ju = max(ju, min(lwin + KU, N - 1));
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq) {
+                        const bool act = pk[qq] == P;
+                        cplx l = a[qq][0] * rinv;
+                        if (!act) l = cplx(0.0, 0.0);
+                        // multipliers by slot (a pivot row keeps only the part below its own
+                        // diagonal), in zgbtf2 order to the scratch, y = b^T U^-1 from the RHS row
+                        st_shared_if(lpn + 32 * P * qq + k, l, pk[qq] >= 0);
+                        st_global_if(Lcol + lg[qq], l, act && lg[qq] <= hi);
+                        if (qq == RW / 32) st_shared_if(sv + col, l, lane == RW % 32);
+#pragma unroll
+                        for (int m = 1; m < P; ++m) {
+                            cplx t = a[qq][m];
+                            submul(t, l, pv[m]);
+                            a[qq][m - 1] = t;
+                        }
+                    }
+                    Lcol += KL - 1;
+                }
+                {
+                    const unsigned m0 = __ballot_sync(0xffffffffu, pk[0] >= 0 && pk[0] < P);
+                    const unsigned m1 = NQ == 2 ? __ballot_sync(0xffffffffu, pk[NQ - 1] >= 0 && pk[NQ - 1] < P) : 0u;
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq)
+                        if (pk[qq] >= 0) S.isp[par * 64 + lane + 32 * qq] = pk[qq] < P;
+                    if (lane == 0) {
+                        S.misc[2 + par] = ju;
+                        S.misc[6 + 2 * par] = (int) m0; S.misc[7 + 2 * par] = (int) m1;
+                        if (info) S.misc[4 + buf] = info;
+                    }
+                }
+                bar_sync_n<BAR_ALL>(NT);
+                if (info) break;
+                jc += P; if (jc >= CW) jc -= CW;
+            }
+        } else {
+            // ============ update warps: U0(t-1), U(t-1), R(t-1), A(t) ============
+            int jc = 0, par = 0;
+            for (int j = 0; j < N; j += P, par ^= 1) {
+                if (j > 0) {
+                    const int jo = j - P;                         // previous panel
+                    const int *opiv = S.pivslot + (par ^ 1) * P;
+                    const unsigned char *oisp = S.isp + (par ^ 1) * 64;
+                    const cplx *lpo = S.lp + (size_t) (par ^ 1) * NS * P;
+                    const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;
+                    int ps[P];
+#pragma unroll
+                    for (int m = 0; m < P; ++m) ps[m] = opiv[m];
+                    // ---- U0(t-1): block t first (two rows x one column per thread), then release
+                    // the panel warp ----
+                    if (tid < P * ((NS + 1) / 2)) {
+                        const int rp = tid / P, m = tid - rp * P;
+                        int ccs = jc + m; if (ccs >= CW) ccs -= CW;
+                        cplx u[P];
+#pragma unroll
+                        for (int k = 0; k < P; ++k) u[k] = S.win[(size_t) ps[k] * CW + ccs];
+#pragma unroll
+                        for (int k = 1; k < P; ++k)
+#pragma unroll
+                            for (int i = 0; i < k; ++i) submul(u[k], lpo[ps[k] * P + i], u[i]);
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            const int s = 2 * rp + r;
+                            if (s < NS && !oisp[s]) {
+                                cplx w = S.win[(size_t) s * CW + ccs];
+#pragma unroll
+                                for (int i = 0; i < P; ++i) submul(w, lpo[s * P + i], u[i]);
+                                S.win[(size_t) s * CW + ccs] = w;
+                            }
+                        }
+                    }
+                    __threadfence_block();
+                    bar_arrive_n<BAR_LOOK>(NT);
+                    // ---- U(t-1): rank-P update of columns jo+2P .. ju(t-1) ----
+                    const int wtrail = S.misc[2 + (par ^ 1)] - (jo + 2 * P) + 1;
+                    int cb = jc + P; if (cb >= CW) cb -= CW;
+                    for (int c0 = 0; c0 < wtrail; c0 += 32) {
+                        const int c = c0 + lane;
+                        if (c < wtrail) {
+                            int ccs = cb + c; if (ccs >= CW) ccs -= CW;
+                            cplx u[P];
+#pragma unroll
+                            for (int m = 0; m < P; ++m) u[m] = S.win[(size_t) ps[m] * CW + ccs];
+#pragma unroll
+                            for (int k = 1; k < P; ++k)
+#pragma unroll
+                                for (int m = 0; m < k; ++m) submul(u[k], lpo[ps[k] * P + m], u[m]);
+                            for (int g = warp; g < W::NG; g += W::NWU) {
+#pragma unroll
+                                for (int r = 0; r < W::RPG; ++r) {
+                                    const int s = g * W::RPG + r;
+                                    if (s < NS && !oisp[s]) {
+                                        cplx w = S.win[(size_t) s * CW + ccs];
+#pragma unroll
+                                        for (int m = 0; m < P; ++m) submul(w, lpo[s * P + m], u[m]);
+                                        S.win[(size_t) s * CW + ccs] = w;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    bar_sync_n<BAR_UPD>(NTU);
+                    // ---- R(t-1): rows jo+RW .. jo+RW+P-1 take the slots of the retired pivot rows ----
+                    int jco = jc - P; if (jco < 0) jco += CW;
+                    for (int e = tid; e < P * CW; e += NTU) {
+                        const int k = e / CW, ccs = e - k * CW;
+                        S.win[(size_t) ps[k] * CW + ccs] = stg[e];
+                    }
+                    // columns jo+CW .. jo+CW+P-1 reuse the retired panel's column slots
+                    for (int e = tid; e < NS * P; e += NTU) {
+                        const int s = e / P, m = e - s * P;
+                        int ccs = jco + m; if (ccs >= CW) ccs -= CW;
+                        const int cn = jo + CW + m;
+                        if (s == RW) S.win[(size_t) RW * CW + ccs] = cn < N ? sv[cn] : cplx(0.0, 0.0);
+                        else if (!oisp[s]) S.win[(size_t) s * CW + ccs] = cplx(0.0, 0.0);
+                    }
+                }
+                // ---- A(t): the block entering after this panel ----
+                const int yI = (j + RW) / 5;
+                compute_coef<W>(K, S, yI + 1 + K.ku, tid, NTU);
+                assemble_block<W>(K, S, km, kn, yI, S.stage + (size_t) par * P * CW, tid, NTU);
+                bar_sync_n<BAR_ALL>(NT);
+                info = S.misc[4 + buf];
+                if (info) break;
+                jc += P; if (jc >= CW) jc -= CW;
+            }
+        }
+        if (tid == 0) { S.misc[buf] = info; if (info) for (int k = 0; k < N; ++k) jpv[k] = 0; }
+        __threadfence();
+        if (buf == 0) bar_arrive_n<BAR_FULL0>(W::NTH); else bar_arrive_n<BAR_FULL1>(W::NTH);
+    }
+}
+
+template <class W>
+int launch_pipe(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
+{
+    const int N = op->A.N;
+    const size_t smem = pipe_smem_bytes<W>(N);
+    if (smem > 227 * 1024) return 1;                 // caller falls back to another kernel
+    static bool configured = false;
+    if (!configured) {
+        SZB_CUDA_OK(cudaFuncSetAttribute(invert_pipe_kernel<W>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    int per_sm = 0;
+    SZB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, invert_pipe_kernel<W>,
+                                                              W::NTH, smem));
+    if (per_sm < 1) return 1;
+    int slots = op->sm_count * per_sm;
+    if (slots > npencil) slots = npencil;
+    const size_t need = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
+    if (need > op->work_bytes) {
+        if (op->d_work) SZB_CUDA_OK(cudaFree(op->d_work));
+        op->d_work = nullptr; op->work_bytes = 0;
+        SZB_CUDA_OK(cudaMalloc(&op->d_work, need));
+        op->work_bytes = need;
+    }
+    op->work_slots = slots;
+    A.lwork = static_cast<cplx *>(op->d_work);
+    invert_pipe_kernel<W><<<slots, W::NTH, smem, stream>>>(A);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// Returns 0 when launched, 1 when this (kl, ku) / size has no instantiation (the
+// caller then uses another kernel), <0 on error.
+int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                         const double *d_km, const double *d_kn, const int *d_index,
+                         cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                         int *d_iters, cudaStream_t stream)
+{
+    PipeArgs A;
+    fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
+    A.npencil = npencil; A.index = d_index;
+    A.state = d_state; A.fs = fs; A.ps = ps;
+    A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
+    A.lwork = nullptr;
+    if (op->A.KL != op->A.KU) return 1;
+    switch (op->A.KL) {
+    case 14: return launch_pipe<PipeCfg<14, 14, 8, 3, 7, 2>>(op, A, npencil, stream);     // k = 4
+    case 24: return launch_pipe<PipeCfg<24, 24, 16, 5, 7, 2>>(op, A, npencil, stream);    // k = 6
+    case 34: return launch_pipe<PipeCfg<34, 34, 16, 6, 7, 2>>(op, A, npencil, stream);    // k = 8
+    case 44: return launch_pipe<PipeCfg<44, 44, 32, 8, 7, 1>>(op, A, npencil, stream);    // k = 10
+    default: return 1;
+    }
+}
+
+}  // namespace szb

@@ -29,6 +29,10 @@ int invert_window_dispatch(const szb_imexop *op, const double phi[2], int npenci
                            const double *d_km, const double *d_kn, const int *d_index,
                            cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                            int *d_iters, cudaStream_t stream);
+int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                         const double *d_km, const double *d_kn, const int *d_index,
+                         cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                         int *d_iters, cudaStream_t stream);
 int invert_blocked_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
