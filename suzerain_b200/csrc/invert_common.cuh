@@ -56,9 +56,28 @@ __device__ __forceinline__ cplx recip_fast(cplx z)
     return recip(z);
 }
 
+// Where the B-spline operator entries D^(d)[yJ, yJ - ku + r] come from: straight from global
+// memory (read-only path), or -- for the row block yI whose three operator rows a kernel
+// staged in shared memory ahead of time, rowblk[d * ld + r] = D^(d) entry with
+// yJ = yI - r + ku -- from there.
+struct DGlobal {
+    const double *D; int n, ld;
+    __device__ __forceinline__ DGlobal(const PackArgs &A) : D(A.D), n(A.n), ld(A.ld) {}
+    __device__ __forceinline__ double operator()(int d, int r, int yJ, int) const
+    { return __ldg(D + (size_t) (d * ld + r) * n + yJ); }
+};
+struct DStaged {
+    const double *D; int n, ld;
+    const double *rowblk; int yI;
+    __device__ __forceinline__ DStaged(const PackArgs &A, const double *rb, int y)
+        : D(A.D), n(A.n), ld(A.ld), rowblk(rb), yI(y) {}
+    __device__ __forceinline__ double operator()(int d, int r, int yJ, int y) const
+    { return y == yI ? rowblk[d * ld + r] : __ldg(D + (size_t) (d * ld + r) * n + yJ); }
+};
+
 // ---- assembled entries of P (M + phi L)^T P^T from the coefficient ring ----
-template <class W>
-__device__ __forceinline__ cplx base_entry(const PackArgs &A, const cplx *s_coef, int I, int J)
+template <class W, class DS>
+__device__ __forceinline__ cplx base_entry(const PackArgs &A, const cplx *s_coef, const DS &ds, int I, int J)
 {
     const int yI = I / 5, sI = I - 5 * yI;
     const int yJ = J / 5, sJ = J - 5 * yJ;
@@ -66,9 +85,7 @@ __device__ __forceinline__ cplx base_entry(const PackArgs &A, const cplx *s_coef
     if (off < -A.ku || off > A.kl) return cplx(0.0, 0.0);
     const int r = A.ku + off;
     const cplx *c = s_coef + (yJ & (W::CR - 1)) * W::NCOEF + (sJ * 5 + sI) * 3;
-    const size_t ds = (size_t) A.ld * A.n;
-    const double *D = A.D + (size_t) r * A.n + yJ;
-    const double m0 = __ldg(D), d1 = __ldg(D + ds), d2 = __ldg(D + 2 * ds);
+    const double m0 = ds(0, r, yJ, yI), d1 = ds(1, r, yJ, yI), d2 = ds(2, r, yJ, yI);
     cplx buf = c[0] * m0;
     buf += c[1] * d1;
     buf += c[2] * d2;
@@ -78,11 +95,11 @@ __device__ __forceinline__ cplx base_entry(const PackArgs &A, const cplx *s_coef
 }
 
 // + NRBC lower-right corner (rholut_imexop.def:505-595)
-template <class W>
-__device__ __forceinline__ cplx nrbc_entry(const PackArgs &A, const cplx *s_coef, double km,
+template <class W, class DS>
+__device__ __forceinline__ cplx nrbc_entry(const PackArgs &A, const cplx *s_coef, const DS &ds, double km,
                                            double kn, int I, int J)
 {
-    cplx X = base_entry<W>(A, s_coef, I, J);
+    cplx X = base_entry<W>(A, s_coef, ds, I, J);
     if (!A.nrbc) return X;
     const int i = I - 5 * (A.n - 3), J0 = 5 * (A.n - 1), j = J - J0;
     if (i < 0 || i >= 15 || j < 0 || j >= 5) return X;
@@ -94,13 +111,13 @@ __device__ __forceinline__ cplx nrbc_entry(const PackArgs &A, const cplx *s_coef
         if (A.nrbc & 4) buf += cplx(A.c[5 * (i - 10) + j], 0.0);
     }
     if (A.nrbc & 4)
-        for (int k = 0; k < 5; ++k) buf -= base_entry<W>(A, s_coef, I, J0 + k) * A.c[j + 5 * k];
+        for (int k = 0; k < 5; ++k) buf -= base_entry<W>(A, s_coef, ds, I, J0 + k) * A.c[j + 5 * k];
     return X + buf;
 }
 
 // + isothermal wall equations (operator_hybrid_isothermal.cpp:470-510)
-template <class W>
-__device__ __forceinline__ cplx assembled_entry(const PackArgs &A, const cplx *s_coef, double km,
+template <class W, class DS>
+__device__ __forceinline__ cplx assembled_entry(const PackArgs &A, const cplx *s_coef, const DS &ds, double km,
                                                 double kn, int I, int J)
 {
     if (A.with_bc) {
@@ -111,14 +128,14 @@ __device__ __forceinline__ cplx assembled_entry(const PackArgs &A, const cplx *s
         if (wall >= 0 && sJ < 4) {
             const int irho = 5 * yJ + 4;
             if (I != J && I != irho) return cplx(0.0, 0.0);
-            cplx s = nrbc_entry<W>(A, s_coef, km, kn, J, J);
+            cplx s = nrbc_entry<W>(A, s_coef, ds, km, kn, J, J);
             if (is_zero(s)) s = cplx(1.0, 0.0);
             if (I == J) return s;
             const double factor = sJ == 0 ? A.E_factor[wall] : A.vel_factor[wall][sJ - 1];
             return -(s * factor);
         }
     }
-    return nrbc_entry<W>(A, s_coef, km, kn, I, J);
+    return nrbc_entry<W>(A, s_coef, ds, km, kn, I, J);
 }
 
 // per-point block coefficients c_{row,col,op}(y) = sum_t alpha_t ref_t(y)
@@ -135,9 +152,23 @@ __device__ __forceinline__ void compute_coef(const PackArgs &A, const SM &S, int
     }
 }
 
-// rows 5*yI .. 5*yI+4, all CW column slots (zeros outside the band), into dst[P][CW]
+// the same from a staged column of the reference profiles, refcol[q] = refs[q][y]
 template <class W, class SM>
-__device__ __forceinline__ void assemble_block(const PackArgs &A, const SM &S, double km,
+__device__ __forceinline__ void compute_coef_staged(const PackArgs &A, const SM &S, int y,
+                                                    const double *refcol, int t0, int nt)
+{
+    if (y < 0 || y >= A.n) return;
+    for (int idx = t0; idx < W::NCOEF; idx += nt) {
+        const int tb = S.tblk[idx], te = S.tblk[idx + 1];
+        cplx c(0.0, 0.0);
+        for (int t = tb; t < te; ++t) c += S.alpha[t] * refcol[S.tref[t]];
+        S.coef[(y & (W::CR - 1)) * W::NCOEF + idx] = c;
+    }
+}
+
+// rows 5*yI .. 5*yI+4, all CW column slots (zeros outside the band), into dst[P][CW]
+template <class W, class SM, class DS>
+__device__ __forceinline__ void assemble_block(const PackArgs &A, const SM &S, const DS &ds, double km,
                                                double kn, int yI, cplx *dst, int t0, int nt)
 {
     for (int e = t0; e < P * W::CW; e += nt) {
@@ -145,8 +176,44 @@ __device__ __forceinline__ void assemble_block(const PackArgs &A, const SM &S, d
         const int I = 5 * yI + sI, J = I - W::KL + ci;        // ci in [0, KV]: in band
         int slot = J % W::CW; if (slot < 0) slot += W::CW;
         cplx v(0.0, 0.0);
-        if (ci <= W::KV && I < A.N && J >= 0 && J < A.N) v = assembled_entry<W>(A, S.coef, km, kn, I, J);
+        if (ci <= W::KV && I < A.N && J >= 0 && J < A.N) v = assembled_entry<W>(A, S.coef, ds, km, kn, I, J);
         dst[sI * W::CW + slot] = v;
+    }
+}
+
+template <class W, class SM>
+__device__ __forceinline__ void assemble_block(const PackArgs &A, const SM &S, double km,
+                                               double kn, int yI, cplx *dst, int t0, int nt)
+{
+    assemble_block<W>(A, S, DGlobal(A), km, kn, yI, dst, t0, nt);
+}
+
+// The same for a row block whose columns touch neither an enforced wall point nor the NRBC
+// corner (yI - kl >= 1, yI + ku <= n - 2): plain operator entries, same arithmetic as
+// base_entry, operator rows from the staged copy rowblk[d * ld + r].
+template <class W, class SM>
+__device__ __forceinline__ void assemble_block_interior(const PackArgs &A, const SM &S,
+                                                        const double *rowblk, int yI, cplx *dst,
+                                                        int t0, int nt)
+{
+#pragma unroll 3
+    for (int e = t0; e < P * W::CW; e += nt) {
+        const int sI = e / W::CW, ci = e - sI * W::CW;
+        const int J = 5 * yI + sI - W::KL + ci;                 // > 0 here
+        const int yJ = J / 5, sJ = J - 5 * yJ;
+        const int r = A.ku + yI - yJ;
+        cplx v(0.0, 0.0);
+        if (ci <= W::KV && r >= 0 && r < A.ld) {
+            const cplx *c = S.coef + (yJ & (W::CR - 1)) * W::NCOEF + (sJ * 5 + sI) * 3;
+            const double m0 = rowblk[r], d1 = rowblk[A.ld + r], d2 = rowblk[2 * A.ld + r];
+            cplx buf = c[0] * m0;
+            buf += c[1] * d1;
+            buf += c[2] * d2;
+            buf = A.phi * buf;
+            if (sI == sJ) buf += cplx(m0, 0.0);
+            v = buf;
+        }
+        dst[sI * W::CW + J % W::CW] = v;
     }
 }
 

@@ -36,26 +36,41 @@
 
 #include "invert_common.cuh"
 
+// Optional phase timing (make PROF=1): per-phase clock64() deltas of the panel warp and of
+// update warp 0, summed over all pencils and CTAs; read back with szb_debug_pipe_prof().
+#ifdef SZB_PIPE_PROF
+__device__ unsigned long long g_pipe_prof[16];
+#define PROF_DECL long long pt0_ = clock64(); long long pacc_[6] = {0, 0, 0, 0, 0, 0};
+#define PROF_MARK(i) do { const long long t_ = clock64(); pacc_[i] += t_ - pt0_; pt0_ = t_; } while (0)
+#define PROF_FLUSH(base, who) do { if (who) for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_pipe_prof[(base) + i_], (unsigned long long) pacc_[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_FLUSH(base, who)
+#endif
+
 namespace szb {
 
 namespace {
 
 using namespace fused;
 
-template <int KL_, int KU_, int CR_, int NWU_, int RPG_, int MINB_>
+template <int KL_, int KU_, int CR_, int NWU_, int NWA_, int RPG_, int MINB_>
 struct PipeCfg {
     static constexpr int MINB = MINB_;              // CTAs per SM the register budget is sized for
+    static constexpr int MAXR = (65536 / (MINB_ * 32 * (NWU_ + NWA_ + 2))) / 8 * 8 > 255 ? 255 : (65536 / (MINB_ * 32 * (NWU_ + NWA_ + 2))) / 8 * 8;
     static constexpr int KL = KL_, KU = KU_, KV = KL_ + KU_;
     static constexpr int RW = KL_ + P + 1;          // matrix row slots (one spare row keeps blocks aligned)
     static constexpr int NS = RW + 1;               // + the right-hand-side row (slot RW)
     static constexpr int NQ = NS > 32 ? 2 : 1;      // row slots per panel-warp lane
     static constexpr int CW = KV + P + 1;           // column slots
     static constexpr int CR = CR_;                  // coefficient ring (collocation points), power of 2
-    static constexpr int NWU = NWU_;                // update warps; warp NWU factors the panels
-    static constexpr int NTU = 32 * NWU_, NT = NTU + 32, NTH = NT + 32;
+    static constexpr int NWU = NWU_, NWA = NWA_;    // update warps, assembly warps; then the panel warp, the solver warp
+    static constexpr int NTU = 32 * NWU_, NTA = 32 * NWA_, NT = NTU + NTA + 32, NTH = NT + 32;
     static constexpr int RPG = RPG_;                // rows per trailing-update task
     static constexpr int NG = (NS + RPG_ - 1) / RPG_;
     static constexpr int NCOEF = 75;
+    static constexpr int LDMAX = 20;                // >= ld of the B-spline operators (2k - 3 <= 17)
     static constexpr int CH = 4, NB = 3;            // solver: L columns per TMA chunk, ring depth
     static_assert(RW % P == 0, "window rows come in groups of five");
     static_assert(NS <= 64, "panel warp holds two row slots per lane");
@@ -74,7 +89,7 @@ template <class W>
 struct PSmem {
     cplx *win;        // [NS][CW]        the window
     cplx *lp;         // [2][NS][P]      per panel parity: multipliers by slot (zeros past a pivot row's own step)
-    cplx *ufx;        // [P][P]          panel warp: fixed-up pivot rows of the previous panel, block t
+    cplx *rec;        // [2][8]          panel warp: the pivot row record of a column step {1/pivot, row tail, label}
     cplx *stage;      // [2][P][CW]      assembled rows waiting to enter
     cplx *coef;       // [CR][75]        per-point block coefficients
     cplx *alpha;      // [MAXTERMS]
@@ -83,19 +98,22 @@ struct PSmem {
     unsigned long long *mbar;   // [NB]
     int *pivslot;     // [2][P]
     int *misc;        // [0..1] info per buffer, [2..3] ju per panel parity, [4..5] panel info per buffer, [6..9] retired-slot mask per panel parity
-    unsigned char *isp;    // [2][64]    slot retired by the panel of that parity
     unsigned char *ipiv;   // [2][N]     jp per column
     unsigned char *tref;   // [MAXTERMS]
     unsigned char *tblk;   // [76]
+    double *drow;     // [2][3][LDMAX]   operator rows of the block assembled in iteration parity p
+    double *refcol;   // [2][32]         reference-profile column for its new coefficient point
 };
 
 template <class W>
 __host__ __device__ inline size_t pipe_smem_bytes(int N)
 {
-    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + 2 * W::NS * P + P * P + 2 * P * W::CW + W::CR * W::NCOEF
+    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + 2 * W::NS * P + 2 * 8 + 2 * P * W::CW + W::CR * W::NCOEF
                                + MAXTERMS + 2 * (size_t) N + W::NB * W::CH * W::KL);
-    b += 8 * W::NB + 4 * (2 * P + 12) + 2 * 64 + 2 * (size_t) N + MAXTERMS + 80;
-    return (b + 15) & ~(size_t) 15;
+    b += 8 * W::NB + 4 * (2 * P + 12) + 2 * (size_t) N + MAXTERMS + 80;
+    b = (b + 15) & ~(size_t) 15;
+    b += 8 * (2 * 3 * W::LDMAX + 2 * 32);
+    return b;
 }
 
 template <class W>
@@ -105,7 +123,7 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
     cplx *p = reinterpret_cast<cplx *>(raw);
     S.win = p;   p += W::NS * W::CW;
     S.lp = p;    p += 2 * W::NS * P;
-    S.ufx = p;   p += P * P;
+    S.rec = p;   p += 2 * 8;
     S.stage = p; p += 2 * P * W::CW;
     S.coef = p;  p += W::CR * W::NCOEF;
     S.alpha = p; p += MAXTERMS;
@@ -115,10 +133,12 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
     S.mbar = reinterpret_cast<unsigned long long *>(q); q += 8 * W::NB;
     S.pivslot = reinterpret_cast<int *>(q); q += 4 * 2 * P;
     S.misc = reinterpret_cast<int *>(q); q += 4 * 12;
-    S.isp = q;  q += 2 * 64;
     S.ipiv = q; q += 2 * (size_t) N;
     S.tref = q; q += MAXTERMS;
-    S.tblk = q;
+    S.tblk = q; q += 80;
+    q = raw + (((size_t) (q - raw) + 15) & ~(size_t) 15);
+    S.drow = reinterpret_cast<double *>(q); q += 8 * 2 * 3 * W::LDMAX;
+    S.refcol = reinterpret_cast<double *>(q);
     return S;
 }
 
@@ -137,6 +157,58 @@ __device__ __forceinline__ void st_shared_if(cplx *p, cplx v, bool pred)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}"
                  :: "r"(smem_u32(p)), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
+}
+
+__device__ __forceinline__ void sts_if(unsigned sa, cplx v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}"
+                 :: "r"(sa), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
+}
+__device__ __forceinline__ void sts2_if(unsigned sa, int x, int y, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
+                 :: "r"(sa), "r"(x), "r"(y), "r"((int) pred) : "memory");
+}
+__device__ __forceinline__ void sts32_if(unsigned sa, int x, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}"
+                 :: "r"(sa), "r"(x), "r"((int) pred) : "memory");
+}
+__device__ __forceinline__ void sts8_if(unsigned sa, int x, bool pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b8 [%0], %1;\n\t}"
+                 :: "r"(sa), "r"(x), "r"((int) pred) : "memory");
+}
+
+// 1/d for d in the normal range, without the special-case branch of the compiler's
+// division: the same MUFU.RCP64H seed and Newton steps as its fast path, so that the
+// panel column step stays one basic block.
+__device__ __forceinline__ double rcp_nr(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
+// Operator rows of row block yI and the reference-profile column of its new coefficient
+// point yI + 1 + ku, into the shared-memory buffers of parity `par`.
+template <class W, class SM>
+__device__ __forceinline__ void stage_rowblock(const PackArgs &K, const SM &S, int yI, int par, int t0, int nt)
+{
+    const int nd = 3 * K.ld;
+    for (int i = t0; i < nd + SZB_NREF + 1; i += nt) {
+        if (i < nd) {
+            const int d = i / K.ld, r = i - d * K.ld, yJ = yI - r + K.ku;
+            S.drow[par * 3 * W::LDMAX + i] = (yJ >= 0 && yJ < K.n) ? __ldg(K.D + (size_t) (d * K.ld + r) * K.n + yJ) : 0.0;
+        } else {
+            const int q = i - nd, yc = yI + 1 + K.ku;
+            S.refcol[par * 32 + q] = yc < K.n ? __ldg(K.refs + (size_t) q * K.n + yc) : 0.0;
+        }
+    }
 }
 
 // The rare exact pivot decision (near ties on the top word, two candidates in one lane,
@@ -169,8 +241,53 @@ __device__ __noinline__ double2 exact_recip(double x, double y)
     return make_double2(r.x, r.y);
 }
 
+// Start of iteration t > 0, all compute warps (the panel warp has nothing else to do until
+// block t is final):
+//   X(t-1)   the five pivot rows of panel t-1 become rows of U, in place, for every trailing
+//            column j .. ju(t-1): one thread per column (unit lower triangular solve with
+//            the pivot rows' own multipliers)
+//   U0(t-1)  block t (columns j .. j+4) of every other row -= its multipliers times those
+//            rows: one thread per (row slot, column)
+// Each ends with a CTA barrier; afterwards the panel warp loads block t and factors it
+// while the update warps do the rest of U(t-1).
+template <class W, class SM>
+__device__ __forceinline__ void lookahead_phases(const SM &S, int j, int jc, int par, int tid)
+{
+    constexpr int NS = W::NS, CW = W::CW, NT = W::NT;
+    const int *opiv = S.pivslot + (par ^ 1) * P;
+    const cplx *lpo = S.lp + (size_t) (par ^ 1) * NS * P;
+    int ps[P];
+#pragma unroll
+    for (int m = 0; m < P; ++m) ps[m] = opiv[m];
+    const int wtot = S.misc[2 + (par ^ 1)] - j + 1;               // columns j .. ju(t-1)
+    for (int c = tid; c < wtot; c += NT) {
+        int ccs = jc + c; if (ccs >= CW) ccs -= CW;
+        cplx u[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) u[k] = S.win[(size_t) ps[k] * CW + ccs];
+#pragma unroll
+        for (int k = 1; k < P; ++k) {
+#pragma unroll
+            for (int i = 0; i < k; ++i) submul(u[k], lpo[ps[k] * P + i], u[i]);
+            S.win[(size_t) ps[k] * CW + ccs] = u[k];
+        }
+    }
+    bar_sync_n<1>(NT);
+    const unsigned long long omask = (unsigned) S.misc[6 + 2 * (par ^ 1)]
+        | (unsigned long long) (unsigned) S.misc[7 + 2 * (par ^ 1)] << 32;
+    for (int e = tid; e < NS * P; e += NT) {
+        const int s = e / P, m = e - s * P;
+        int ccs = jc + m; if (ccs >= CW) ccs -= CW;
+        cplx w = S.win[(size_t) s * CW + ccs];
+#pragma unroll
+        for (int i = 0; i < P; ++i) submul(w, lpo[s * P + i], S.win[(size_t) ps[i] * CW + ccs]);
+        st_shared_if(S.win + (size_t) s * CW + ccs, w, !((omask >> s) & 1));
+    }
+    bar_sync_n<1>(NT);
+}
+
 template <class W>
-__global__ void __launch_bounds__(W::NTH, W::MINB)
+__global__ void __maxnreg__(W::MAXR)
 invert_pipe_kernel(const PipeArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -180,7 +297,7 @@ invert_pipe_kernel(const PipeArgs A)
     const int tid = threadIdx.x;
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
     constexpr int NQ = W::NQ;
-    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_LOOK = 7;
+    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
 
@@ -280,7 +397,8 @@ invert_pipe_kernel(const PipeArgs A)
 
     // ============================ compute warps ============================
     const int lane = tid & 31, warp = tid >> 5;
-    const bool panel = warp == W::NWU;
+    constexpr int ROLE_UPDATE = 0, ROLE_ASSEMBLE = 1, ROLE_PANEL = 2;
+    const int role = warp < W::NWU ? ROLE_UPDATE : warp < W::NWU + W::NWA ? ROLE_ASSEMBLE : ROLE_PANEL;
     int q = 0;
     for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
         const int buf = q & 1;
@@ -306,7 +424,6 @@ invert_pipe_kernel(const PipeArgs A)
         for (int t = tid; t < K.terms->nterms; t += NT)
             S.alpha[t] = wave_factor(K.terms->wave[t], km, kn) * K.terms->sc[t];
         if (tid == 0) { S.misc[buf] = 0; S.misc[4 + buf] = 0; }
-        if (tid < 2 * 64) S.isp[tid] = 0;
         bar_sync_n<BAR_ALL>(NT);
         for (int y = 0; y <= RW / 5 + K.ku; ++y) compute_coef<W>(K, S, y, tid, NT);
         bar_sync_n<BAR_ALL>(NT);
@@ -314,10 +431,12 @@ invert_pipe_kernel(const PipeArgs A)
         for (int blk = 0; blk < RW / 5; ++blk)
             assemble_block<W>(K, S, km, kn, blk, S.win + (size_t) blk * P * CW, tid, NT);
         for (int c = tid; c < CW; c += NT) S.win[(size_t) RW * CW + c] = c < N ? sv[c] : cplx(0.0, 0.0);
+        // operator rows / profile column for the first block assembled inside the panel loop
+        stage_rowblock<W>(K, S, RW / 5, 0, tid, NT);
         bar_sync_n<BAR_ALL>(NT);
 
         int info = 0;
-        if (panel) {
+        if (role == ROLE_PANEL) {
             // ====================== panel warp: F(t) ======================
             // Row slot lane + 32 q lives in this lane.  lg: the logical row the slot holds
             // (INT_MAX for the right-hand side and for absent slots: never a candidate);
@@ -332,11 +451,14 @@ invert_pipe_kernel(const PipeArgs A)
                 lg[qq] = slot < RW ? slot : INT_MAX;
                 pk[qq] = slot < NS ? P : -1;
             }
+            const unsigned rec_sa = smem_u32(S.rec), sv_sa = smem_u32(sv), jpv_sa = smem_u32(jpv);
             int ju = 0, jc = 0, par = 0;
+            PROF_DECL
             for (int j = 0; j < N; j += P, par ^= 1) {
                 // block t of every row: entering rows from the stage, the others from the
-                // window once the update warps have applied panel t-1 to it
-                if (j > 0) bar_sync_n<BAR_LOOK>(NT);
+                // window once panel t-1 has been applied to it
+                if (j > 0) lookahead_phases<W>(S, j, jc, par, tid);
+                PROF_MARK(0);
                 {
                     const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;
                     int cs[P];
@@ -353,13 +475,17 @@ invert_pipe_kernel(const PipeArgs A)
                         if (ret) { lg[qq] = j - P + RW + pk[qq]; pk[qq] = P; }
                     }
                 }
-                cplx *lpn = S.lp + (size_t) par * NS * P + lane * P;      // + 32 P q: this lane's slots
+                PROF_MARK(1);
+                const unsigned lp_sa = smem_u32(S.lp + (size_t) par * NS * P + lane * P);   // + 32 P q
+                const unsigned piv_sa = smem_u32(S.pivslot + par * P);
                 cplx *Lcol = Lg + (size_t) j * KL - (j + 1);                // L(lg, col) at Lcol[lg]
 #pragma unroll 1
                 for (int k = 0; k < P; ++k) {
                     const int col = j + k, hi = min(col + KL, N - 1);
-                    // izamax over rows col..hi on the top 32 bits of |re|+|im|; anything but a
-                    // unique, comfortably scaled maximum takes the exact path
+                    // izamax over rows col..hi on the top 32 bits of |re|+|im|.  The lanes whose
+                    // candidate carries the maximal top word publish their row, its reciprocal
+                    // pivot and its label straight away; if that maximum was not unique or not
+                    // comfortably scaled the exact decision below overrides them.
                     int h[NQ];
                     double mag[NQ];
 #pragma unroll
@@ -368,54 +494,57 @@ invert_pipe_kernel(const PipeArgs A)
                         h[qq] = (pk[qq] == P && lg[qq] <= hi) ? __double2hiint(mag[qq]) : -1;
                     }
                     const bool sq = NQ == 2 && h[NQ - 1] > h[0];
-                    const int mh = __reduce_max_sync(0xffffffffu, sq ? h[NQ - 1] : h[0]);
-                    // every lane inverts its own better candidate while the search is in flight
                     const cplx cb = sq ? a[NQ - 1][0] : a[0][0];
-                    cplx rsp;
-                    {
-                        const double d = 1.0 / fma(cb.x, cb.x, cb.y * cb.y);
-                        rsp = cplx(cb.x * d, -cb.y * d);
-                    }
-                    const unsigned b0 = __ballot_sync(0xffffffffu, h[0] == mh);
-                    const unsigned b1 = NQ == 2 ? __ballot_sync(0xffffffffu, h[NQ - 1] == mh) : 0u;
+                    const double rd = rcp_nr(fma(cb.x, cb.x, cb.y * cb.y));
+                    cplx rsp(cb.x * rd, -cb.y * rd);
+                    const int mh = __reduce_max_sync(0xffffffffu, sq ? h[NQ - 1] : h[0]);
+                    const bool p0 = h[0] == mh, p1 = NQ == 2 && h[NQ - 1] == mh;
+                    const unsigned b0 = __ballot_sync(0xffffffffu, p0);
+                    const unsigned b1 = NQ == 2 ? __ballot_sync(0xffffffffu, p1) : 0u;
                     const unsigned ball = b0 | b1;
-                    int src, wq;
+                    const unsigned recw = rec_sa + (k & 1) * 8 * (unsigned) sizeof(cplx);
+                    sts_if(recw, rsp, p0 || p1);
+#pragma unroll
+                    for (int m = 1; m < P; ++m) {
+                        sts_if(recw + m * 16, a[0][m], p0);
+                        if (NQ == 2) sts_if(recw + m * 16, a[NQ - 1][m], p1);
+                    }
+                    sts2_if(recw + 5 * 16, lg[0], lane, p0);
+                    if (NQ == 2) sts2_if(recw + 5 * 16, lg[NQ - 1], lane + 32, p1);
                     bool zp = false;
                     // 0x22f00000 ~ 1e-140, 0x5d000000 ~ 1e+140
-                    if (mh >= 0x22f00000 && mh <= 0x5d000000 && (b0 & b1) == 0 && (ball & (ball - 1)) == 0) {
-                        src = __ffs(ball) - 1;
-                        wq = b1 != 0;
-                    } else {
+                    if (!(mh >= 0x22f00000 && mh <= 0x5d000000 && (b0 & b1) == 0 && (ball & (ball - 1)) == 0)) {
                         const long long key0 = h[0] >= 0 ? __double_as_longlong(mag[0]) : -1ll;
                         const long long key1 = NQ == 2 && h[NQ - 1] >= 0 ? __double_as_longlong(mag[NQ - 1]) : -1ll;
                         const int e = exact_pivot(key0, key1, lg[0], lg[NQ - 1]);
-                        src = e & 0xff; wq = (e >> 8) & 1; zp = (e >> 16) & 1;
-                        const cplx ce = (e >> 24) ? a[NQ - 1][0] : a[0][0];
-                        const double2 r = exact_recip(ce.x, ce.y);
-                        rsp = cplx(r.x, r.y);
+                        const int src = e & 0xff, wq = (e >> 8) & 1;
+                        zp = (e >> 16) & 1;
+                        __syncwarp();
+                        if (lane == src) {
+                            const cplx ce = wq ? a[NQ - 1][0] : a[0][0];
+                            const double2 r = exact_recip(ce.x, ce.y);
+                            sts_if(recw, cplx(r.x, r.y), true);
+#pragma unroll
+                            for (int m = 1; m < P; ++m) sts_if(recw + m * 16, wq ? a[NQ - 1][m] : a[0][m], true);
+                            sts2_if(recw + 5 * 16, wq ? lg[NQ - 1] : lg[0], lane + 32 * wq, true);
+                        }
                     }
-                    const cplx rinv = shfl_c(rsp, src);
+                    __syncwarp();
+                    const cplx *rec = S.rec + (k & 1) * 8;
+                    const cplx rinv = rec[0];
                     cplx pv[P];
-                    int lwin;
-                    if (NQ == 2 && wq) {                           // warp-uniform
 #pragma unroll
-                        for (int m = 1; m < P; ++m) pv[m] = shfl_c(a[NQ - 1][m], src);
-                        lwin = __shfl_sync(0xffffffffu, lg[NQ - 1], src);
-                    } else {
-#pragma unroll
-                        for (int m = 1; m < P; ++m) pv[m] = shfl_c(a[0][m], src);
-                        lwin = __shfl_sync(0xffffffffu, lg[0], src);
-                    }
+                    for (int m = 1; m < P; ++m) pv[m] = rec[m];
+                    const int2 lw = *reinterpret_cast<const int2 *>(rec + 5);
+                    const int lwin = lw.x, wslot = lw.y;
                     // interchange = relabel: the slot holding row `col` takes the winner's label
 #pragma unroll
                     for (int qq = 0; qq < NQ; ++qq) {
                         if (pk[qq] == P && lg[qq] == col) lg[qq] = lwin;
-                        if (lane == src && wq == qq) { pk[qq] = k; lg[qq] = col; }
+                        if (lane + 32 * qq == wslot) { pk[qq] = k; lg[qq] = col; }
                     }
-                    if (lane == 0) {
-                        jpv[col] = (unsigned char) (lwin - col);
-                        S.pivslot[par * P + k] = src + 32 * wq;
-                    }
+                    sts8_if(jpv_sa + col, lwin - col, lane == 0);
+                    sts32_if(piv_sa + 4 * k, wslot, lane == 0);
                     if (zp) { info = col + 1; break; }             // |re|+|im| == 0: zero pivot
                     ju = max(ju, min(lwin + KU, N - 1));
 #pragma unroll
@@ -425,9 +554,9 @@ invert_pipe_kernel(const PipeArgs A)
                         if (!act) l = cplx(0.0, 0.0);
                         // multipliers by slot (a pivot row keeps only the part below its own
                         // diagonal), in zgbtf2 order to the scratch, y = b^T U^-1 from the RHS row
-                        st_shared_if(lpn + 32 * P * qq + k, l, pk[qq] >= 0);
+                        sts_if(lp_sa + 16 * (32 * P * qq + k), l, pk[qq] >= 0);
                         st_global_if(Lcol + lg[qq], l, act && lg[qq] <= hi);
-                        if (qq == RW / 32) st_shared_if(sv + col, l, lane == RW % 32);
+                        if (qq == RW / 32) sts_if(sv_sa + 16 * col, l, lane == RW % 32);
 #pragma unroll
                         for (int m = 1; m < P; ++m) {
                             cplx t = a[qq][m];
@@ -437,61 +566,43 @@ invert_pipe_kernel(const PipeArgs A)
                     }
                     Lcol += KL - 1;
                 }
+                PROF_MARK(2);
                 {
                     const unsigned m0 = __ballot_sync(0xffffffffu, pk[0] >= 0 && pk[0] < P);
                     const unsigned m1 = NQ == 2 ? __ballot_sync(0xffffffffu, pk[NQ - 1] >= 0 && pk[NQ - 1] < P) : 0u;
-#pragma unroll
-                    for (int qq = 0; qq < NQ; ++qq)
-                        if (pk[qq] >= 0) S.isp[par * 64 + lane + 32 * qq] = pk[qq] < P;
                     if (lane == 0) {
                         S.misc[2 + par] = ju;
                         S.misc[6 + 2 * par] = (int) m0; S.misc[7 + 2 * par] = (int) m1;
                         if (info) S.misc[4 + buf] = info;
                     }
                 }
+                PROF_MARK(3);
                 bar_sync_n<BAR_ALL>(NT);
+                PROF_MARK(4);
                 if (info) break;
                 jc += P; if (jc >= CW) jc -= CW;
             }
-        } else {
-            // ============ update warps: U0(t-1), U(t-1), R(t-1), A(t) ============
+            PROF_FLUSH(0, lane == 0);
+        } else if (role == ROLE_UPDATE) {
+            // ============ update warps: X/U0(t-1) with everybody, U(t-1), R(t-1) ============
             int jc = 0, par = 0;
+            PROF_DECL
             for (int j = 0; j < N; j += P, par ^= 1) {
                 if (j > 0) {
+                    lookahead_phases<W>(S, j, jc, par, tid);
+                    PROF_MARK(0);
                     const int jo = j - P;                         // previous panel
                     const int *opiv = S.pivslot + (par ^ 1) * P;
-                    const unsigned char *oisp = S.isp + (par ^ 1) * 64;
                     const cplx *lpo = S.lp + (size_t) (par ^ 1) * NS * P;
                     const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;
+                    const unsigned long long omask = (unsigned) S.misc[6 + 2 * (par ^ 1)]
+                        | (unsigned long long) (unsigned) S.misc[7 + 2 * (par ^ 1)] << 32;
                     int ps[P];
 #pragma unroll
                     for (int m = 0; m < P; ++m) ps[m] = opiv[m];
-                    // ---- U0(t-1): block t first (two rows x one column per thread), then release
-                    // the panel warp ----
-                    if (tid < P * ((NS + 1) / 2)) {
-                        const int rp = tid / P, m = tid - rp * P;
-                        int ccs = jc + m; if (ccs >= CW) ccs -= CW;
-                        cplx u[P];
-#pragma unroll
-                        for (int k = 0; k < P; ++k) u[k] = S.win[(size_t) ps[k] * CW + ccs];
-#pragma unroll
-                        for (int k = 1; k < P; ++k)
-#pragma unroll
-                            for (int i = 0; i < k; ++i) submul(u[k], lpo[ps[k] * P + i], u[i]);
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            const int s = 2 * rp + r;
-                            if (s < NS && !oisp[s]) {
-                                cplx w = S.win[(size_t) s * CW + ccs];
-#pragma unroll
-                                for (int i = 0; i < P; ++i) submul(w, lpo[s * P + i], u[i]);
-                                S.win[(size_t) s * CW + ccs] = w;
-                            }
-                        }
-                    }
-                    __threadfence_block();
-                    bar_arrive_n<BAR_LOOK>(NT);
-                    // ---- U(t-1): rank-P update of columns jo+2P .. ju(t-1) ----
+                    // ---- U(t-1): rank-P update of columns jo+2P .. ju(t-1); the pivot rows already
+                    // hold rows of U.  One warp per row group, one lane per column; the next row's
+                    // operands are fetched while the current one is updated. ----
                     const int wtrail = S.misc[2 + (par ^ 1)] - (jo + 2 * P) + 1;
                     int cb = jc + P; if (cb >= CW) cb -= CW;
                     for (int c0 = 0; c0 < wtrail; c0 += 32) {
@@ -501,44 +612,81 @@ invert_pipe_kernel(const PipeArgs A)
                             cplx u[P];
 #pragma unroll
                             for (int m = 0; m < P; ++m) u[m] = S.win[(size_t) ps[m] * CW + ccs];
-#pragma unroll
-                            for (int k = 1; k < P; ++k)
-#pragma unroll
-                                for (int m = 0; m < k; ++m) submul(u[k], lpo[ps[k] * P + m], u[m]);
                             for (int g = warp; g < W::NG; g += W::NWU) {
+                                const int s0 = g * W::RPG;
+                                cplx wn = S.win[(size_t) s0 * CW + ccs], ln[P];
+#pragma unroll
+                                for (int m = 0; m < P; ++m) ln[m] = lpo[s0 * P + m];
 #pragma unroll
                                 for (int r = 0; r < W::RPG; ++r) {
-                                    const int s = g * W::RPG + r;
-                                    if (s < NS && !oisp[s]) {
-                                        cplx w = S.win[(size_t) s * CW + ccs];
+                                    const int s = s0 + r;
+                                    cplx w = wn, l[P];
 #pragma unroll
-                                        for (int m = 0; m < P; ++m) submul(w, lpo[s * P + m], u[m]);
-                                        S.win[(size_t) s * CW + ccs] = w;
+                                    for (int m = 0; m < P; ++m) l[m] = ln[m];
+                                    if (r + 1 < W::RPG) {
+                                        const int sn = min(s + 1, NS - 1);
+                                        wn = S.win[(size_t) sn * CW + ccs];
+#pragma unroll
+                                        for (int m = 0; m < P; ++m) ln[m] = lpo[sn * P + m];
                                     }
+#pragma unroll
+                                    for (int m = 0; m < P; ++m) submul(w, l[m], u[m]);
+                                    st_shared_if(S.win + (size_t) min(s, NS - 1) * CW + ccs, w,
+                                                 s < NS && !((omask >> s) & 1));
                                 }
                             }
                         }
                     }
+                    PROF_MARK(1);
                     bar_sync_n<BAR_UPD>(NTU);
-                    // ---- R(t-1): rows jo+RW .. jo+RW+P-1 take the slots of the retired pivot rows ----
+                    PROF_MARK(2);
+                    // ---- R(t-1): rows jo+RW .. jo+RW+P-1 take the slots of the retired pivot rows;
+                    // columns jo+CW .. jo+CW+P-1 reuse the retired panel's column slots ----
                     int jco = jc - P; if (jco < 0) jco += CW;
-                    for (int e = tid; e < P * CW; e += NTU) {
-                        const int k = e / CW, ccs = e - k * CW;
-                        S.win[(size_t) ps[k] * CW + ccs] = stg[e];
-                    }
-                    // columns jo+CW .. jo+CW+P-1 reuse the retired panel's column slots
-                    for (int e = tid; e < NS * P; e += NTU) {
-                        const int s = e / P, m = e - s * P;
+                    constexpr int RC = (P * CW + NTU - 1) / NTU, RZ = (NS * P + NTU - 1) / NTU;
+                    cplx cp[RC];
+#pragma unroll
+                    for (int i = 0; i < RC; ++i) cp[i] = stg[min(tid + i * NTU, P * CW - 1)];
+#pragma unroll
+                    for (int i = 0; i < RZ; ++i) {
+                        const int e = tid + i * NTU, s = e / P, m = e - s * P;
                         int ccs = jco + m; if (ccs >= CW) ccs -= CW;
                         const int cn = jo + CW + m;
-                        if (s == RW) S.win[(size_t) RW * CW + ccs] = cn < N ? sv[cn] : cplx(0.0, 0.0);
-                        else if (!oisp[s]) S.win[(size_t) s * CW + ccs] = cplx(0.0, 0.0);
+                        if (e < NS * P) {
+                            if (s == RW) S.win[(size_t) RW * CW + ccs] = cn < N ? sv[cn] : cplx(0.0, 0.0);
+                            else if (!((omask >> s) & 1)) S.win[(size_t) s * CW + ccs] = cplx(0.0, 0.0);
+                        }
                     }
+#pragma unroll
+                    for (int i = 0; i < RC; ++i) {
+                        const int e = tid + i * NTU, k = e / CW, ccs = e - k * CW;
+                        if (e < P * CW) S.win[(size_t) opiv[k] * CW + ccs] = cp[i];
+                    }
+                    PROF_MARK(3);
                 }
-                // ---- A(t): the block entering after this panel ----
+                bar_sync_n<BAR_ALL>(NT);
+                PROF_MARK(5);
+                info = S.misc[4 + buf];
+                if (info) break;
+                jc += P; if (jc >= CW) jc -= CW;
+            }
+            PROF_FLUSH(8, tid == 0);
+        } else {
+            // ============ assembly warps: X/U0(t-1) with everybody, A(t) ============
+            const int ta = tid - NTU;
+            int jc = 0, par = 0;
+            for (int j = 0; j < N; j += P, par ^= 1) {
+                if (j > 0) lookahead_phases<W>(S, j, jc, par, tid);
+                // ---- A(t): the block entering after this panel, from the staged operator rows
+                // and profile column; then stage the next iteration's ----
                 const int yI = (j + RW) / 5;
-                compute_coef<W>(K, S, yI + 1 + K.ku, tid, NTU);
-                assemble_block<W>(K, S, km, kn, yI, S.stage + (size_t) par * P * CW, tid, NTU);
+                compute_coef_staged<W>(K, S, yI + 1 + K.ku, S.refcol + par * 32, ta, W::NTA);
+                cplx *dst = S.stage + (size_t) par * P * CW;
+                if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
+                    assemble_block_interior<W>(K, S, S.drow + par * 3 * W::LDMAX, yI, dst, ta, W::NTA);
+                else
+                    assemble_block<W>(K, S, DStaged(K, S.drow + par * 3 * W::LDMAX, yI), km, kn, yI, dst, ta, W::NTA);
+                stage_rowblock<W>(K, S, yI + 1, par ^ 1, ta, W::NTA);
                 bar_sync_n<BAR_ALL>(NT);
                 info = S.misc[4 + buf];
                 if (info) break;
@@ -601,12 +749,26 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     A.lwork = nullptr;
     if (op->A.KL != op->A.KU) return 1;
     switch (op->A.KL) {
-    case 14: return launch_pipe<PipeCfg<14, 14, 8, 3, 7, 2>>(op, A, npencil, stream);     // k = 4
-    case 24: return launch_pipe<PipeCfg<24, 24, 16, 5, 7, 2>>(op, A, npencil, stream);    // k = 6
-    case 34: return launch_pipe<PipeCfg<34, 34, 16, 6, 7, 2>>(op, A, npencil, stream);    // k = 8
-    case 44: return launch_pipe<PipeCfg<44, 44, 32, 8, 7, 1>>(op, A, npencil, stream);    // k = 10
+    case 14: return launch_pipe<PipeCfg<14, 14, 8, 3, 1, 7, 2>>(op, A, npencil, stream);     // k = 4
+    case 24: return launch_pipe<PipeCfg<24, 24, 16, 4, 2, 8, 2>>(op, A, npencil, stream);    // k = 6
+    case 34: return launch_pipe<PipeCfg<34, 34, 16, 4, 2, 11, 2>>(op, A, npencil, stream);    // k = 8
+    case 44: return launch_pipe<PipeCfg<44, 44, 32, 6, 2, 9, 1>>(op, A, npencil, stream);    // k = 10
     default: return 1;
     }
 }
 
 }  // namespace szb
+
+// debug hook (not part of the C ABI): phase clocks accumulated by a PROF=1 build
+extern "C" int szb_debug_pipe_prof(unsigned long long out[16], int reset)
+{
+#ifdef SZB_PIPE_PROF
+    if (cudaMemcpyFromSymbol(out, g_pipe_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_pipe_prof, z, sizeof z); }
+    return 1;
+#else
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    (void) reset;
+    return 0;
+#endif
+}

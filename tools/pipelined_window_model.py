@@ -4,8 +4,9 @@
 Same blocked right-looking banded LU on a sliding, slot-indirected shared-memory window as
 tools/blocked_window_model.py, but scheduled as a two-stage pipeline per panel t (j = 5 t):
 
-    update warps : U0(t-1) rank-5 update of block t (columns j .. j+4) of the window, then signal
-    panel warp   : (wait)  load block t of every row (entering rows from the stage)
+    all warps    : X(t-1)  the pivot rows of panel t-1 become rows of U in place (columns j .. ju)
+                   U0(t-1) rank-5 update of block t (columns j .. j+4) of the window
+    panel warp   : load block t of every row (entering rows from the stage)
                    F(t)    factor panel t in registers, publish multipliers / pivot slots
     update warps : U(t-1)  rank-5 update of columns j+5 .. ju(t-1) in the window
                    R(t-1)  rows entering after panel t-1 replace the retired pivot rows,
@@ -77,7 +78,6 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
     pivslot = Shared("pivslot", (2, P), log, dtype=int)
     juv = Shared("ju", (2,), log, dtype=int)
     sv = Shared("sv", (N,), log)
-    ufx = np.zeros((P, P), dtype=complex)       # panel-warp private exchange buffer
 
     def A_entry(i, c):
         return entry(i, c) if (0 <= i < N and 0 <= c < N and -KL <= c - i <= KU) else 0.0
@@ -101,7 +101,6 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
 
     # panel-warp registers
     a = np.zeros((NS, P), dtype=complex)
-    lprev = np.zeros((NS, P), dtype=complex)
     lg = np.array([s if s < RW else -10**9 for s in range(NS)])
     pk = np.full(NS, P)
     ju = 0
@@ -172,13 +171,20 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
             jo = j - P
             ops = [pivslot[par ^ 1, k] for k in range(P)]
             c_lo, c_hi = (jo + P, jo + 2 * P - 1) if lookahead else (jo + 2 * P, N)
+            if lookahead:
+                # ---- phase 1: the pivot rows of panel t-1 become rows of U, in place, for every
+                # trailing column (one thread per column) ----
+                for c in range(jo + P, juv[par ^ 1] + 1):
+                    cs = c % CW
+                    u = [W[ops[m], cs] for m in range(P)]
+                    for k in range(1, P):
+                        for m in range(k):
+                            u[k] -= lp[par ^ 1, ops[k], m] * u[m]
+                        W[ops[k], cs] = u[k]
             # ---- U(t-1): columns c_lo .. c_hi ----
             for c in range(c_lo, min(c_hi, juv[par ^ 1]) + 1):
                 cs = c % CW
                 u = [W[ops[m], cs] for m in range(P)]
-                for k in range(1, P):
-                    for m in range(k):
-                        u[k] -= lp[par ^ 1, ops[k], m] * u[m]
                 for s in range(NS):
                     if isp[par ^ 1, s]:
                         continue

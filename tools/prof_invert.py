@@ -28,3 +28,13 @@ for rep in range(2):
     y = torch.zeros_like(st)
     t0.record(); op.accumulate_batch(case.phi, km, kn, st, 0.0, y); t1.record(); torch.cuda.synchronize()
     print(f"accumulate {t0.elapsed_time(t1):.3f} ms")
+import ctypes
+_lib = ctypes.CDLL(os.path.join(ROOT, "suzerain_b200", "libsuzerain_b200.so"))
+if hasattr(_lib, "szb_debug_pipe_prof"):
+    buf = (ctypes.c_ulonglong * 16)()
+    if _lib.szb_debug_pipe_prof(buf, 1) == 1:
+        # three invert launches happened above per rep x 2 reps; report per pencil-panel
+        n = 4 * len(case.km) * (5 * case.n // 5)
+        names = ["P:lookahead", "P:load", "P:F", "P:publish", "P:endbar", "-", "-", "-",
+                 "U:lookahead", "U:main", "U:barupd", "U:R", "U:A", "U:endbar"]
+        print("phase clocks per panel:", {k: round(buf[i] / n) for i, k in enumerate(names) if k != "-"})
