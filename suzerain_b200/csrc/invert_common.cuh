@@ -75,6 +75,15 @@ struct DStaged {
     { return y == yI ? rowblk[d * ld + r] : __ldg(D + (size_t) (d * ld + r) * n + yJ); }
 };
 
+// Coefficient ring layout: c_{row sJ, col sI, op d}(y) at coef_index(y, sJ, sI, d).  sJ runs
+// fastest, then the ring slot of y: a warp assembling consecutive columns J = 5 yJ + sJ of one
+// matrix row (fixed sI) reads consecutive addresses.
+template <class W>
+__device__ __forceinline__ int coef_index(int y, int sJ, int sI, int d)
+{
+    return ((d * 5 + sI) * W::CR + (y & (W::CR - 1))) * 5 + sJ;
+}
+
 // ---- assembled entries of P (M + phi L)^T P^T from the coefficient ring ----
 template <class W, class DS>
 __device__ __forceinline__ cplx base_entry(const PackArgs &A, const cplx *s_coef, const DS &ds, int I, int J)
@@ -84,11 +93,10 @@ __device__ __forceinline__ cplx base_entry(const PackArgs &A, const cplx *s_coef
     const int off = yI - yJ;
     if (off < -A.ku || off > A.kl) return cplx(0.0, 0.0);
     const int r = A.ku + off;
-    const cplx *c = s_coef + (yJ & (W::CR - 1)) * W::NCOEF + (sJ * 5 + sI) * 3;
     const double m0 = ds(0, r, yJ, yI), d1 = ds(1, r, yJ, yI), d2 = ds(2, r, yJ, yI);
-    cplx buf = c[0] * m0;
-    buf += c[1] * d1;
-    buf += c[2] * d2;
+    cplx buf = s_coef[coef_index<W>(yJ, sJ, sI, 0)] * m0;
+    buf += s_coef[coef_index<W>(yJ, sJ, sI, 1)] * d1;
+    buf += s_coef[coef_index<W>(yJ, sJ, sI, 2)] * d2;
     buf = A.phi * buf;
     if (sI == sJ) buf += cplx(m0, 0.0);
     return buf;
@@ -148,7 +156,7 @@ __device__ __forceinline__ void compute_coef(const PackArgs &A, const SM &S, int
         const int tb = S.tblk[idx], te = S.tblk[idx + 1];
         cplx c(0.0, 0.0);
         for (int t = tb; t < te; ++t) c += S.alpha[t] * __ldg(A.refs + (size_t) S.tref[t] * A.n + y);
-        S.coef[(y & (W::CR - 1)) * W::NCOEF + idx] = c;
+        S.coef[coef_index<W>(y, idx / 15, (idx / 3) % 5, idx % 3)] = c;
     }
 }
 
@@ -162,7 +170,7 @@ __device__ __forceinline__ void compute_coef_staged(const PackArgs &A, const SM 
         const int tb = S.tblk[idx], te = S.tblk[idx + 1];
         cplx c(0.0, 0.0);
         for (int t = tb; t < te; ++t) c += S.alpha[t] * refcol[S.tref[t]];
-        S.coef[(y & (W::CR - 1)) * W::NCOEF + idx] = c;
+        S.coef[coef_index<W>(y, idx / 15, (idx / 3) % 5, idx % 3)] = c;
     }
 }
 
@@ -204,11 +212,10 @@ __device__ __forceinline__ void assemble_block_interior(const PackArgs &A, const
         const int r = A.ku + yI - yJ;
         cplx v(0.0, 0.0);
         if (ci <= W::KV && r >= 0 && r < A.ld) {
-            const cplx *c = S.coef + (yJ & (W::CR - 1)) * W::NCOEF + (sJ * 5 + sI) * 3;
             const double m0 = rowblk[r], d1 = rowblk[A.ld + r], d2 = rowblk[2 * A.ld + r];
-            cplx buf = c[0] * m0;
-            buf += c[1] * d1;
-            buf += c[2] * d2;
+            cplx buf = S.coef[coef_index<W>(yJ, sJ, sI, 0)] * m0;
+            buf += S.coef[coef_index<W>(yJ, sJ, sI, 1)] * d1;
+            buf += S.coef[coef_index<W>(yJ, sJ, sI, 2)] * d2;
             buf = A.phi * buf;
             if (sI == sJ) buf += cplx(m0, 0.0);
             v = buf;

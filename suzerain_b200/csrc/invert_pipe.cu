@@ -58,22 +58,33 @@ using namespace fused;
 template <int KL_, int KU_, int CR_, int NWU_, int NWA_, int RPG_, int MINB_>
 struct PipeCfg {
     static constexpr int MINB = MINB_;              // CTAs per SM the register budget is sized for
-    static constexpr int MAXR = (65536 / (MINB_ * 32 * (NWU_ + NWA_ + 2))) / 8 * 8 > 255 ? 255 : (65536 / (MINB_ * 32 * (NWU_ + NWA_ + 2))) / 8 * 8;
+    static constexpr int NWALLOC = (NWU_ + NWA_ + ((KL_ + 5 + 2) > 32 ? 2 : 1) + 1 + 3) / 4 * 4;      // warps are allocated in fours
+    static constexpr int MAXR = (65536 / (MINB_ * 32 * NWALLOC)) / 8 * 8 > 255 ? 255 : (65536 / (MINB_ * 32 * NWALLOC)) / 8 * 8;
     static constexpr int KL = KL_, KU = KU_, KV = KL_ + KU_;
     static constexpr int RW = KL_ + P + 1;          // matrix row slots (one spare row keeps blocks aligned)
     static constexpr int NS = RW + 1;               // + the right-hand-side row (slot RW)
-    static constexpr int NQ = NS > 32 ? 2 : 1;      // row slots per panel-warp lane
+    static constexpr int NWP = NS > 32 ? 2 : 1;     // panel warps: one row slot per lane
     static constexpr int CW = KV + P + 1;           // column slots
     static constexpr int CR = CR_;                  // coefficient ring (collocation points), power of 2
-    static constexpr int NWU = NWU_, NWA = NWA_;    // update warps, assembly warps; then the panel warp, the solver warp
-    static constexpr int NTU = 32 * NWU_, NTA = 32 * NWA_, NT = NTU + NTA + 32, NTH = NT + 32;
+    static constexpr int NWU = NWU_, NWA = NWA_;    // update warps, assembly warps; then the panel warps, the solver warp
+    static constexpr int NTU = 32 * NWU_, NTA = 32 * NWA_, NT = NTU + NTA + 32 * NWP, NTH = NT + 32;
     static constexpr int RPG = RPG_;                // rows per trailing-update task
     static constexpr int NG = (NS + RPG_ - 1) / RPG_;
     static constexpr int NCOEF = 75;
     static constexpr int LDMAX = 20;                // >= ld of the B-spline operators (2k - 3 <= 17)
     static constexpr int CH = 4, NB = 3;            // solver: L columns per TMA chunk, ring depth
+    // Physical warp w runs on sub-partition w % 4.  With twelve warps (6 update, 3 assembly,
+    // 2 panel, 1 solver; logical order U0-5 A0-2 P0-1 S) the layout is
+    //   sub-partition 0: P0 A0 A2   1: P1 A1 S   2: U0 U2 U4   3: U1 U3 U5
+    __host__ __device__ static constexpr int logical_warp(int w)
+    {
+        if (NWU_ == 6 && NWA_ == 3 && NWP == 2) {
+            return (int) ((0x54b8327610a9ull >> (4 * w)) & 0xf);      // {9, 10, 0, 1, 6, 7, 2, 3, 8, 11, 4, 5}
+        }
+        return w;
+    }
     static_assert(RW % P == 0, "window rows come in groups of five");
-    static_assert(NS <= 64, "panel warp holds two row slots per lane");
+    static_assert(NS <= 64, "at most two panel warps");
     static_assert((CR & (CR - 1)) == 0, "ring size must be a power of two");
 };
 
@@ -89,7 +100,7 @@ template <class W>
 struct PSmem {
     cplx *win;        // [NS][CW]        the window
     cplx *lp;         // [2][NS][P]      per panel parity: multipliers by slot (zeros past a pivot row's own step)
-    cplx *rec;        // [2][8]          panel warp: the pivot row record of a column step {1/pivot, row tail, label}
+    cplx *rec;        // [2][2][8]       per column parity and panel warp: its pivot row record {1/pivot, row tail, label}
     cplx *stage;      // [2][P][CW]      assembled rows waiting to enter
     cplx *coef;       // [CR][75]        per-point block coefficients
     cplx *alpha;      // [MAXTERMS]
@@ -97,7 +108,8 @@ struct PSmem {
     cplx *lring;      // [NB][CH*KL]     multipliers prefetched by TMA for the solver warp
     unsigned long long *mbar;   // [NB]
     int *pivslot;     // [2][P]
-    int *misc;        // [0..1] info per buffer, [2..3] ju per panel parity, [4..5] panel info per buffer, [6..9] retired-slot mask per panel parity
+    int *misc;        // [0..1] info per buffer, [2..3] ju per panel parity, [4..5] panel info per buffer, [6..9] retired-slot mask per panel parity,
+                      // [12..19] per column parity and panel warp {top word, ok}, [20..27] exact keys {key, row}
     unsigned char *ipiv;   // [2][N]     jp per column
     unsigned char *tref;   // [MAXTERMS]
     unsigned char *tblk;   // [76]
@@ -108,9 +120,9 @@ struct PSmem {
 template <class W>
 __host__ __device__ inline size_t pipe_smem_bytes(int N)
 {
-    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + 2 * W::NS * P + 2 * 8 + 2 * P * W::CW + W::CR * W::NCOEF
+    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + 2 * W::NS * P + 2 * 2 * 8 + 2 * P * W::CW + W::CR * W::NCOEF
                                + MAXTERMS + 2 * (size_t) N + W::NB * W::CH * W::KL);
-    b += 8 * W::NB + 4 * (2 * P + 12) + 2 * (size_t) N + MAXTERMS + 80;
+    b += 8 * W::NB + 4 * (2 * P + 32) + 2 * (size_t) N + MAXTERMS + 80;
     b = (b + 15) & ~(size_t) 15;
     b += 8 * (2 * 3 * W::LDMAX + 2 * 32);
     return b;
@@ -123,7 +135,7 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
     cplx *p = reinterpret_cast<cplx *>(raw);
     S.win = p;   p += W::NS * W::CW;
     S.lp = p;    p += 2 * W::NS * P;
-    S.rec = p;   p += 2 * 8;
+    S.rec = p;   p += 2 * 2 * 8;
     S.stage = p; p += 2 * P * W::CW;
     S.coef = p;  p += W::CR * W::NCOEF;
     S.alpha = p; p += MAXTERMS;
@@ -132,7 +144,7 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
     unsigned char *q = reinterpret_cast<unsigned char *>(p);
     S.mbar = reinterpret_cast<unsigned long long *>(q); q += 8 * W::NB;
     S.pivslot = reinterpret_cast<int *>(q); q += 4 * 2 * P;
-    S.misc = reinterpret_cast<int *>(q); q += 4 * 12;
+    S.misc = reinterpret_cast<int *>(q); q += 4 * 32;
     S.ipiv = q; q += 2 * (size_t) N;
     S.tref = q; q += MAXTERMS;
     S.tblk = q; q += 80;
@@ -180,9 +192,32 @@ __device__ __forceinline__ void sts8_if(unsigned sa, int x, bool pred)
                  :: "r"(sa), "r"(x), "r"((int) pred) : "memory");
 }
 
+__device__ __forceinline__ cplx lds_c(unsigned sa)
+{
+    cplx v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sa) : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 lds_i2(unsigned sa)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sa) : "memory");
+    return v;
+}
+// keep a value in a register instead of letting the compiler recompute it (S2R / LDC chains)
+// inside the panel warp's column loop
+__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
+
 // 1/d for d in the normal range, without the special-case branch of the compiler's
 // division: the same MUFU.RCP64H seed and Newton steps as its fast path, so that the
 // panel column step stays one basic block.
+__device__ __forceinline__ double rcp_seed(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+}
 __device__ __forceinline__ double rcp_nr(double d)
 {
     double r;
@@ -294,10 +329,12 @@ invert_pipe_kernel(const PipeArgs A)
     const PackArgs &K = A.pk;
     const int N = K.N, n = K.n;
     const PSmem<W> S = pipe_carve<W>(smem_raw, N);
-    const int tid = threadIdx.x;
+    // logical thread index: warps are dealt to the four SM sub-partitions round-robin, so the
+    // roles are permuted to keep the latency-critical panel warps away from the FP64-heavy
+    // update warps (see PipeCfg::logical_warp)
+    const int tid = W::logical_warp(threadIdx.x >> 5) * 32 + (threadIdx.x & 31);
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
-    constexpr int NQ = W::NQ;
-    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6;
+    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_PP = 7;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
 
@@ -437,21 +474,24 @@ invert_pipe_kernel(const PipeArgs A)
 
         int info = 0;
         if (role == ROLE_PANEL) {
-            // ====================== panel warp: F(t) ======================
-            // Row slot lane + 32 q lives in this lane.  lg: the logical row the slot holds
-            // (INT_MAX for the right-hand side and for absent slots: never a candidate);
-            // pk: P while the row is in play, 0..P-1 once it is this panel's pivot row,
-            // -1 for absent slots.  a[q][0] is the column being eliminated; finished columns
+            // ====================== panel warps: F(t) ======================
+            // Row slot lane + 32 pw lives in lane `lane` of panel warp pw.  lg: the logical row
+            // the slot holds (INT_MAX for the right-hand side and for absent slots: never a
+            // candidate); pk: P while the row is in play, 0..P-1 once it is this panel's pivot
+            // row, -1 for absent slots.  a[0] is the column being eliminated; finished columns
             // are shifted out so that the column loop is one body (instruction-cache footprint).
-            int lg[NQ], pk[NQ];
-            cplx a[NQ][P];
-#pragma unroll
-            for (int qq = 0; qq < NQ; ++qq) {
-                const int slot = lane + 32 * qq;
-                lg[qq] = slot < RW ? slot : INT_MAX;
-                pk[qq] = slot < NS ? P : -1;
-            }
-            const unsigned rec_sa = smem_u32(S.rec), sv_sa = smem_u32(sv), jpv_sa = smem_u32(jpv);
+            constexpr bool TWO = W::NWP == 2;
+            const int pw = warp - (W::NWU + W::NWA);
+            const int slot = lane + 32 * pw;
+            int lg = slot < RW ? slot : INT_MAX;
+            int pk = slot < NS ? P : -1;
+            cplx a[P];
+            unsigned rec_sa = smem_u32(S.rec), sv_sa = smem_u32(sv), jpv_sa = smem_u32(jpv);
+            unsigned xmh_sa = smem_u32(S.misc + 12);
+            pin(rec_sa); pin(sv_sa); pin(jpv_sa); pin(xmh_sa);
+            // (b) lane predicates as pinned registers (the compiler otherwise re-reads SR_TID)
+            int is_lead = tid == NTU + W::NTA, is_rhs = slot == RW, is_l0 = lane == 0;
+            pin(is_lead); pin(is_rhs); pin(is_l0);
             int ju = 0, jc = 0, par = 0;
             PROF_DECL
             for (int j = 0; j < N; j += P, par ^= 1) {
@@ -461,119 +501,149 @@ invert_pipe_kernel(const PipeArgs A)
                 PROF_MARK(0);
                 {
                     const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;
-                    int cs[P];
+                    const bool ret = pk >= 0 && pk < P;
+                    const cplx *src = ret ? stg + pk * CW : S.win + (size_t) (pk >= 0 ? slot : 0) * CW;
 #pragma unroll
-                    for (int m = 0; m < P; ++m) { cs[m] = jc + m; if (cs[m] >= CW) cs[m] -= CW; }
-#pragma unroll
-                    for (int qq = 0; qq < NQ; ++qq) {
-                        const bool ret = pk[qq] >= 0 && pk[qq] < P;
-                        const cplx *src = ret ? stg + pk[qq] * CW
-                                              : S.win + (size_t) (pk[qq] >= 0 ? lane + 32 * qq : 0) * CW;
-#pragma unroll
-                        for (int m = 0; m < P; ++m) a[qq][m] = src[cs[m]];
-                        // a row that retired in the previous panel was replaced by row j-P+RW+k
-                        if (ret) { lg[qq] = j - P + RW + pk[qq]; pk[qq] = P; }
+                    for (int m = 0; m < P; ++m) {
+                        int c = jc + m; if (c >= CW) c -= CW;
+                        a[m] = src[c];
                     }
+                    // a row that retired in the previous panel was replaced by row j-P+RW+k
+                    // (rows past the end of the matrix are never candidates)
+                    if (ret) { lg = j - P + RW + pk; if (lg >= N) lg = INT_MAX; pk = P; }
                 }
                 PROF_MARK(1);
-                const unsigned lp_sa = smem_u32(S.lp + (size_t) par * NS * P + lane * P);   // + 32 P q
-                const unsigned piv_sa = smem_u32(S.pivslot + par * P);
+                unsigned lp_sa = smem_u32(S.lp + (size_t) par * NS * P + slot * P);
+                unsigned piv_sa = smem_u32(S.pivslot + par * P);
+                pin(lp_sa); pin(piv_sa);
                 cplx *Lcol = Lg + (size_t) j * KL - (j + 1);                // L(lg, col) at Lcol[lg]
+                // Every lane inverts its candidate of the coming column while the current one is being
+                // eliminated (1/z = conj(z) / |z|^2 for z comfortably scaled; anything else takes the
+                // exact path): the seed and first residual at the end of a column step, the Newton
+                // steps next to the pivot search of the following one.
+                double rd_d = fma(a[0].x, a[0].x, a[0].y * a[0].y), rd_r = rcp_seed(rd_d);
+                double rd_e = fma(-rd_d, rd_r, 1.0);
 #pragma unroll 1
                 for (int k = 0; k < P; ++k) {
-                    const int col = j + k, hi = min(col + KL, N - 1);
-                    // izamax over rows col..hi on the top 32 bits of |re|+|im|.  The lanes whose
-                    // candidate carries the maximal top word publish their row, its reciprocal
-                    // pivot and its label straight away; if that maximum was not unique or not
-                    // comfortably scaled the exact decision below overrides them.
-                    int h[NQ];
-                    double mag[NQ];
-#pragma unroll
-                    for (int qq = 0; qq < NQ; ++qq) {
-                        mag[qq] = cabs1(a[qq][0]);
-                        h[qq] = (pk[qq] == P && lg[qq] <= hi) ? __double2hiint(mag[qq]) : -1;
+                    const int col = j + k, hi = col + KL;
+                    // izamax over rows col..hi on the top 32 bits of |re|+|im|.  In each panel warp
+                    // the lane whose candidate carries the warp's maximal top word publishes its row,
+                    // the reciprocal pivot and its label straight away, and lane 0 the top word itself
+                    // (+ whether it is unique and comfortably scaled: 0x22f00000 ~ 1e-140,
+                    // 0x5d000000 ~ 1e+140); the warps then pick the larger one.  Anything else
+                    // (ties on the top word, tiny / huge / zero pivots) takes the exact path.
+                    const double mag = cabs1(a[0]);
+                    cplx rs;
+                    {
+                        double e = fma(rd_e, rd_e, rd_e), r = fma(rd_r, e, rd_r);
+                        e = fma(-rd_d, r, 1.0);
+                        r = fma(r, e, r);
+                        rs = cplx(a[0].x * r, -a[0].y * r);
                     }
-                    const bool sq = NQ == 2 && h[NQ - 1] > h[0];
-                    const cplx cb = sq ? a[NQ - 1][0] : a[0][0];
-                    const double rd = rcp_nr(fma(cb.x, cb.x, cb.y * cb.y));
-                    cplx rsp(cb.x * rd, -cb.y * rd);
-                    const int mh = __reduce_max_sync(0xffffffffu, sq ? h[NQ - 1] : h[0]);
-                    const bool p0 = h[0] == mh, p1 = NQ == 2 && h[NQ - 1] == mh;
-                    const unsigned b0 = __ballot_sync(0xffffffffu, p0);
-                    const unsigned b1 = NQ == 2 ? __ballot_sync(0xffffffffu, p1) : 0u;
-                    const unsigned ball = b0 | b1;
-                    const unsigned recw = rec_sa + (k & 1) * 8 * (unsigned) sizeof(cplx);
-                    sts_if(recw, rsp, p0 || p1);
+                    const int h = (pk == P && lg <= hi) ? __double2hiint(mag) : -1;
+                    const int mh = __reduce_max_sync(0xffffffffu, h);
+                    const bool p = h == mh && h >= 0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, p);
+                    const int okw = mh < 0 || ((bal & (bal - 1)) == 0 && mh >= 0x22f00000 && mh <= 0x5d000000);
+                    const unsigned recw = rec_sa + ((k & 1) * 2 + pw) * 8 * (unsigned) sizeof(cplx);
+                    sts_if(recw, rs, p);
 #pragma unroll
-                    for (int m = 1; m < P; ++m) {
-                        sts_if(recw + m * 16, a[0][m], p0);
-                        if (NQ == 2) sts_if(recw + m * 16, a[NQ - 1][m], p1);
-                    }
-                    sts2_if(recw + 5 * 16, lg[0], lane, p0);
-                    if (NQ == 2) sts2_if(recw + 5 * 16, lg[NQ - 1], lane + 32, p1);
-                    bool zp = false;
-                    // 0x22f00000 ~ 1e-140, 0x5d000000 ~ 1e+140
-                    if (!(mh >= 0x22f00000 && mh <= 0x5d000000 && (b0 & b1) == 0 && (ball & (ball - 1)) == 0)) {
-                        const long long key0 = h[0] >= 0 ? __double_as_longlong(mag[0]) : -1ll;
-                        const long long key1 = NQ == 2 && h[NQ - 1] >= 0 ? __double_as_longlong(mag[NQ - 1]) : -1ll;
-                        const int e = exact_pivot(key0, key1, lg[0], lg[NQ - 1]);
-                        const int src = e & 0xff, wq = (e >> 8) & 1;
-                        zp = (e >> 16) & 1;
+                    for (int m = 1; m < P; ++m) sts_if(recw + m * 16, a[m], p);
+                    sts2_if(recw + 5 * 16, lg, slot, p);
+                    int g = 0, fast = okw && mh >= 0;
+                    if (TWO) {
+                        sts2_if(xmh_sa + ((k & 1) * 2 + pw) * 8, mh, okw, is_l0);
+                        bar_sync_n<BAR_PP>(64);
+                        const int2 x0 = lds_i2(xmh_sa + (k & 1) * 16), x1 = lds_i2(xmh_sa + (k & 1) * 16 + 8);
+                        g = x1.x > x0.x;
+                        fast = x0.x != x1.x && (g ? x1.y : x0.y);
+                    } else {
                         __syncwarp();
-                        if (lane == src) {
-                            const cplx ce = wq ? a[NQ - 1][0] : a[0][0];
-                            const double2 r = exact_recip(ce.x, ce.y);
+                    }
+                    bool zp = false;
+                    if (!fast) {
+                        // exact: first maximum of the full 64-bit |re|+|im|, smallest row on ties
+                        const long long key = h >= 0 ? __double_as_longlong(mag) : -1ll;
+                        const int e = exact_pivot(key, -1ll, lg, INT_MAX);
+                        const int src = e & 0xff;
+                        long long kwin = __shfl_sync(0xffffffffu, key, src);
+                        int lgw = __shfl_sync(0xffffffffu, lg, src);
+                        if ((e >> 16) & 1) { if (kwin < 0) lgw = INT_MAX; }      // no candidate here / zero
+                        const unsigned xk_sa = xmh_sa + 32 + pw * 16;
+                        if (TWO) {
+                            if (lane == 0) {
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(xk_sa), "r"((int) (kwin & 0xffffffffll)), "r"((int) (kwin >> 32)) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" :: "r"(xk_sa + 8), "r"(lgw) : "memory");
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == src && kwin >= 0) {
+                            const double2 r = exact_recip(a[0].x, a[0].y);
                             sts_if(recw, cplx(r.x, r.y), true);
 #pragma unroll
-                            for (int m = 1; m < P; ++m) sts_if(recw + m * 16, wq ? a[NQ - 1][m] : a[0][m], true);
-                            sts2_if(recw + 5 * 16, wq ? lg[NQ - 1] : lg[0], lane + 32 * wq, true);
+                            for (int m = 1; m < P; ++m) sts_if(recw + m * 16, a[m], true);
+                            sts2_if(recw + 5 * 16, lg, slot, true);
+                        }
+                        if (TWO) {
+                            bar_sync_n<BAR_PP>(64);
+                            const int2 ka = lds_i2(xmh_sa + 32), kb = lds_i2(xmh_sa + 48);
+                            const int la = lds_i2(xmh_sa + 40).x, lb = lds_i2(xmh_sa + 56).x;
+                            const long long k0 = (long long) (unsigned) ka.x | (long long) ka.y << 32;
+                            const long long k1 = (long long) (unsigned) kb.x | (long long) kb.y << 32;
+                            g = k1 > k0 || (k1 == k0 && lb < la);
+                            zp = (g ? k1 : k0) <= 0;
+                        } else {
+                            __syncwarp();
+                            zp = kwin <= 0;
                         }
                     }
-                    __syncwarp();
-                    const cplx *rec = S.rec + (k & 1) * 8;
-                    const cplx rinv = rec[0];
+                    const unsigned recg = rec_sa + ((k & 1) * 2 + g) * 8 * (unsigned) sizeof(cplx);
+                    const cplx rinv = lds_c(recg);
                     cplx pv[P];
 #pragma unroll
-                    for (int m = 1; m < P; ++m) pv[m] = rec[m];
-                    const int2 lw = *reinterpret_cast<const int2 *>(rec + 5);
-                    const int lwin = lw.x, wslot = lw.y;
+                    for (int m = 1; m < P; ++m) pv[m] = lds_c(recg + 16 * m);
+                    const int2 lw = lds_i2(recg + 16 * 5);
+                    int lwin = lw.x;
+                    const int wslot = lw.y;
+                    if (zp) lwin = col;
                     // interchange = relabel: the slot holding row `col` takes the winner's label
-#pragma unroll
-                    for (int qq = 0; qq < NQ; ++qq) {
-                        if (pk[qq] == P && lg[qq] == col) lg[qq] = lwin;
-                        if (lane + 32 * qq == wslot) { pk[qq] = k; lg[qq] = col; }
-                    }
-                    sts8_if(jpv_sa + col, lwin - col, lane == 0);
-                    sts32_if(piv_sa + 4 * k, wslot, lane == 0);
+                    if (pk == P && lg == col) lg = lwin;
+                    if (slot == wslot && !zp) { pk = k; lg = col; }
+                    sts8_if(jpv_sa + col, lwin - col, is_lead);
+                    sts32_if(piv_sa + 4 * k, wslot, is_lead);
                     if (zp) { info = col + 1; break; }             // |re|+|im| == 0: zero pivot
-                    ju = max(ju, min(lwin + KU, N - 1));
-#pragma unroll
-                    for (int qq = 0; qq < NQ; ++qq) {
-                        const bool act = pk[qq] == P;
-                        cplx l = a[qq][0] * rinv;
+                    ju = max(ju, lwin + KU);
+                    {
+                        const bool act = pk == P;
+                        cplx l = a[0] * rinv;
                         if (!act) l = cplx(0.0, 0.0);
                         // multipliers by slot (a pivot row keeps only the part below its own
                         // diagonal), in zgbtf2 order to the scratch, y = b^T U^-1 from the RHS row
-                        sts_if(lp_sa + 16 * (32 * P * qq + k), l, pk[qq] >= 0);
-                        st_global_if(Lcol + lg[qq], l, act && lg[qq] <= hi);
-                        if (qq == RW / 32) sts_if(sv_sa + 16 * col, l, lane == RW % 32);
+                        sts_if(lp_sa + 16 * k, l, pk >= 0);
+                        st_global_if(Lcol + lg, l, act && lg <= hi);
+                        sts_if(sv_sa + 16 * col, l, is_rhs);
 #pragma unroll
                         for (int m = 1; m < P; ++m) {
-                            cplx t = a[qq][m];
+                            cplx t = a[m];
                             submul(t, l, pv[m]);
-                            a[qq][m - 1] = t;
+                            a[m - 1] = t;
                         }
+                        rd_d = fma(a[0].x, a[0].x, a[0].y * a[0].y);
+                        rd_r = rcp_seed(rd_d);
+                        rd_e = fma(-rd_d, rd_r, 1.0);
                     }
                     Lcol += KL - 1;
                 }
                 PROF_MARK(2);
                 {
-                    const unsigned m0 = __ballot_sync(0xffffffffu, pk[0] >= 0 && pk[0] < P);
-                    const unsigned m1 = NQ == 2 ? __ballot_sync(0xffffffffu, pk[NQ - 1] >= 0 && pk[NQ - 1] < P) : 0u;
+                    const unsigned m = __ballot_sync(0xffffffffu, pk >= 0 && pk < P);
                     if (lane == 0) {
-                        S.misc[2 + par] = ju;
-                        S.misc[6 + 2 * par] = (int) m0; S.misc[7 + 2 * par] = (int) m1;
-                        if (info) S.misc[4 + buf] = info;
+                        S.misc[6 + 2 * par + pw] = (int) m;
+                        if (!TWO) S.misc[7 + 2 * par] = 0;
+                        if (pw == 0) {
+                            S.misc[2 + par] = min(ju, N - 1);
+                            if (info) S.misc[4 + buf] = info;
+                        }
                     }
                 }
                 PROF_MARK(3);
@@ -582,7 +652,7 @@ invert_pipe_kernel(const PipeArgs A)
                 if (info) break;
                 jc += P; if (jc >= CW) jc -= CW;
             }
-            PROF_FLUSH(0, lane == 0);
+            PROF_FLUSH(0, lane == 0 && pw == 0);
         } else if (role == ROLE_UPDATE) {
             // ============ update warps: X/U0(t-1) with everybody, U(t-1), R(t-1) ============
             int jc = 0, par = 0;
@@ -605,6 +675,7 @@ invert_pipe_kernel(const PipeArgs A)
                     // operands are fetched while the current one is updated. ----
                     const int wtrail = S.misc[2 + (par ^ 1)] - (jo + 2 * P) + 1;
                     int cb = jc + P; if (cb >= CW) cb -= CW;
+#ifndef SZB_PIPE_NOUPD
                     for (int c0 = 0; c0 < wtrail; c0 += 32) {
                         const int c = c0 + lane;
                         if (c < wtrail) {
@@ -637,6 +708,7 @@ invert_pipe_kernel(const PipeArgs A)
                             }
                         }
                     }
+#endif
                     PROF_MARK(1);
                     bar_sync_n<BAR_UPD>(NTU);
                     PROF_MARK(2);
@@ -682,10 +754,12 @@ invert_pipe_kernel(const PipeArgs A)
                 const int yI = (j + RW) / 5;
                 compute_coef_staged<W>(K, S, yI + 1 + K.ku, S.refcol + par * 32, ta, W::NTA);
                 cplx *dst = S.stage + (size_t) par * P * CW;
+#ifndef SZB_PIPE_NOUPD
                 if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
                     assemble_block_interior<W>(K, S, S.drow + par * 3 * W::LDMAX, yI, dst, ta, W::NTA);
                 else
                     assemble_block<W>(K, S, DStaged(K, S.drow + par * 3 * W::LDMAX, yI), km, kn, yI, dst, ta, W::NTA);
+#endif
                 stage_rowblock<W>(K, S, yI + 1, par ^ 1, ta, W::NTA);
                 bar_sync_n<BAR_ALL>(NT);
                 info = S.misc[4 + buf];
@@ -751,7 +825,7 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     switch (op->A.KL) {
     case 14: return launch_pipe<PipeCfg<14, 14, 8, 3, 1, 7, 2>>(op, A, npencil, stream);     // k = 4
     case 24: return launch_pipe<PipeCfg<24, 24, 16, 4, 2, 8, 2>>(op, A, npencil, stream);    // k = 6
-    case 34: return launch_pipe<PipeCfg<34, 34, 16, 4, 2, 11, 2>>(op, A, npencil, stream);    // k = 8
+    case 34: return launch_pipe<PipeCfg<34, 34, 16, 6, 3, 7, 2>>(op, A, npencil, stream);    // k = 8
     case 44: return launch_pipe<PipeCfg<44, 44, 32, 6, 2, 9, 1>>(op, A, npencil, stream);    // k = 10
     default: return 1;
     }
