@@ -75,11 +75,13 @@ struct PipeCfg {
     static constexpr int CH = 4, NB = 3;            // solver: L columns per TMA chunk, ring depth
     // Physical warp w runs on sub-partition w % 4.  With twelve warps (6 update, 3 assembly,
     // 2 panel, 1 solver; logical order U0-5 A0-2 P0-1 S) the layout is
-    //   sub-partition 0: P0 A0 A2   1: P1 A1 S   2: U0 U2 U4   3: U1 U3 U5
+    //   sub-partition 0: P0 U0 U1   1: P1 U2 S   2: A0 A1 U3   3: A2 U4 U5
+    // (measured: the assembly warps, not the update warps, slow a panel warp they share a
+    // sub-partition with)
     __host__ __device__ static constexpr int logical_warp(int w)
     {
         if (NWU_ == 6 && NWA_ == 3 && NWP == 2) {
-            return (int) ((0x54b8327610a9ull >> (4 * w)) & 0xf);      // {9, 10, 0, 1, 6, 7, 2, 3, 8, 11, 4, 5}
+            return (int) ((0x53b1472086a9ull >> (4 * w)) & 0xf);      // {9, 10, 6, 8, 0, 2, 7, 4, 1, 11, 3, 5}
         }
         return w;
     }
@@ -675,7 +677,7 @@ invert_pipe_kernel(const PipeArgs A)
                     // operands are fetched while the current one is updated. ----
                     const int wtrail = S.misc[2 + (par ^ 1)] - (jo + 2 * P) + 1;
                     int cb = jc + P; if (cb >= CW) cb -= CW;
-#ifndef SZB_PIPE_NOUPD
+#if !defined(SZB_PIPE_NOUPD) || SZB_PIPE_NOUPD == 2
                     for (int c0 = 0; c0 < wtrail; c0 += 32) {
                         const int c = c0 + lane;
                         if (c < wtrail) {
@@ -754,7 +756,7 @@ invert_pipe_kernel(const PipeArgs A)
                 const int yI = (j + RW) / 5;
                 compute_coef_staged<W>(K, S, yI + 1 + K.ku, S.refcol + par * 32, ta, W::NTA);
                 cplx *dst = S.stage + (size_t) par * P * CW;
-#ifndef SZB_PIPE_NOUPD
+#if !defined(SZB_PIPE_NOUPD) || SZB_PIPE_NOUPD == 1
                 if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
                     assemble_block_interior<W>(K, S, S.drow + par * 3 * W::LDMAX, yI, dst, ta, W::NTA);
                 else

@@ -153,6 +153,37 @@ def test_invert_heavy_pivoting(dev, phi, solver):
     assert pc.relmax(got["x"], want["x"]) <= 1e-10
 
 
+@pytest.mark.parametrize("k", [8, 10])
+@pytest.mark.parametrize("phi", [-50.0, -5 + 3j, 0.3j])
+def test_invert_heavy_pivoting_two_panel_warps(dev, k, phi):
+    """Orders 8 and 10 need more than 32 window rows, i.e. two panel warps in the pipelined
+    kernel (invert_pipe.cu): the pivot of a column is then decided across warps, and with
+    |phi| = O(1..50) most decisions are non-trivial interchanges, many of them near ties."""
+    case = pc.make_case("tiny_16x24x16", max_pencils=30, phi=complex(phi), k=k, Ny=48)
+    got = pc.gpu_invert(case, "zgbsv", dev)
+    want = pc.oracle_invert(case, "zgbsv")
+    nontrivial = (want["ipiv"] != np.arange(1, want["ipiv"].shape[1] + 1)).mean()
+    assert nontrivial > 0.3
+    assert np.all(got["info"] == 0) and want["info"] == 0
+    assert np.array_equal(got["ipiv"], want["ipiv"]), "pivot choices differ"
+    assert pc.relmax(got["x"], want["x"]) <= 1e-10
+
+
+def test_invert_singular_reports_info_two_panel_warps(dev):
+    """zgbtrf's info (first zero pivot) out of the cross-warp exact pivot decision."""
+    import suzerain_b200 as sz
+    case = pc.make_case("tiny_16x24x16", max_pencils=6, k=8, Ny=40)
+    bop = case.bop
+    st = bop.storage.copy()
+    st[0] = 0.0                                  # M = 0 and phi = 0: singular past the wall columns
+    bad = sz.BsplineOp.from_storage(bop.k, bop.n, bop.nderiv, bop.kl, bop.ku, st)
+    case2 = pc.Case(case.name, bad, case.refs, case.scenario, case.walls, None, case.km, case.kn,
+                    case.x, 0j, False)
+    got = pc.gpu_invert(case2, "zgbsv", dev)
+    assert np.all(got["info"] == pc.oracle_invert(case2, "zgbsv")["info"])
+    assert np.allclose(got["x"], case.x.reshape(len(case.km), -1))      # state untouched
+
+
 def test_invert_window_many_pencils(dev):
     """More pencils than resident CTAs x 2: every slot reuses both of its buffers."""
     case = pc.make_case("tiny_16x24x16", npencils=6000)
