@@ -203,7 +203,8 @@ struct FieldCtx {
     int nx = 0, nz = 0, xa = 0, npencil = 0, nact = 0;
     int zero_zero = -1;                     // position of the (0,0) pencil in the active list
     std::vector<int> active_idx, inactive_idx;
-    std::vector<Chunk> chunks;
+    std::vector<Chunk> chunks;              // transfer-bound calls (apply, accumulate): eight equal chunks
+    std::vector<Chunk> chunks_inv;          // invert: short first and last chunk, two long ones
     DevBuf<double> d_km, d_kn;
     DevBuf<int> d_act, d_info;
     DevBuf<szb_complex> d_a, d_b;           // interleaved mirror, contiguous-state mirror
@@ -255,16 +256,36 @@ int build_ctx(const szb_wavegrid *g, FieldCtx &F)
     }
     row_a0[F.nz] = (int) F.active_idx.size();
     F.nact = (int) F.active_idx.size();
-    // chunks of consecutive active rows, about eight per call
+    // Chunks of consecutive active rows.  apply / accumulate are transfer-bound: eight equal
+    // chunks keep upload, compute and download overlapped.  For invert every chunk is one
+    // launch of the persistent kernel and pays its tail (slots idling until the slowest pencil
+    // of the chunk is done) while only the first upload and the last download are exposed: a
+    // short first and last chunk (1/16 of the rows each) and two long ones in between.
     int nrows_active = 0;
     for (int r = 0; r < F.nz; ++r) nrows_active += row_active[r];
-    const int per = nrows_active ? (nrows_active + 7) / 8 : 1;
-    for (int r = 0; r < F.nz;) {
-        if (!row_active[r]) { ++r; continue; }
-        int e = r;
-        while (e < F.nz && row_active[e] && e - r < per) ++e;
-        F.chunks.push_back(Chunk{ r, e - r, row_a0[r], row_a0[e] });
-        r = e;
+    auto cut = [&](std::vector<int> sizes, std::vector<Chunk> &out) {
+        size_t si = 0;
+        for (int r = 0; r < F.nz;) {
+            if (!row_active[r]) { ++r; continue; }
+            const int per = si < sizes.size() ? std::max(sizes[si], 1) : nrows_active;
+            int e = r;
+            while (e < F.nz && row_active[e] && e - r < per) ++e;
+            // an inactive row inside the range ends the chunk early: carry the rest over
+            if (si < sizes.size()) {
+                const int done = e - r;
+                if (done < per && si + 1 < sizes.size()) sizes[si + 1] += per - done;
+                ++si;
+            }
+            out.push_back(Chunk{ r, e - r, row_a0[r], row_a0[e] });
+            r = e;
+        }
+    };
+    cut(std::vector<int>(8, nrows_active ? (nrows_active + 7) / 8 : 1), F.chunks);
+    if (nrows_active >= 32) {
+        const int edge = nrows_active / 16, mid = nrows_active - 2 * edge;
+        cut({ edge, (mid + 1) / 2, mid / 2, edge }, F.chunks_inv);
+    } else {
+        F.chunks_inv = F.chunks;
     }
     SZB_CUDA_OK(F.d_km.alloc(akm.size())); SZB_CUDA_OK(F.d_kn.alloc(akn.size()));
     SZB_CUDA_OK(F.d_act.alloc(F.active_idx.size())); SZB_CUDA_OK(F.d_info.alloc(F.nact + 1));
@@ -276,7 +297,8 @@ int build_ctx(const szb_wavegrid *g, FieldCtx &F)
     SZB_CUDA_OK(cudaStreamCreateWithFlags(&F.s_in, cudaStreamNonBlocking));
     SZB_CUDA_OK(cudaStreamCreateWithFlags(&F.s_comp, cudaStreamNonBlocking));
     SZB_CUDA_OK(cudaStreamCreateWithFlags(&F.s_out, cudaStreamNonBlocking));
-    F.ev_in.resize(F.chunks.size()); F.ev_done.resize(F.chunks.size());
+    const size_t nev = std::max(F.chunks.size(), F.chunks_inv.size());
+    F.ev_in.resize(nev); F.ev_done.resize(nev);
     for (auto &e : F.ev_in) SZB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : F.ev_done) SZB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SZB_CUDA_OK(cudaEventCreateWithFlags(&F.ev_prev, cudaEventDisableTiming));
@@ -446,8 +468,8 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
         SZB_CUDA_OK(cudaMemcpyAsync(ic0, dic.p, sizeof(szb_complex) * N * nconstraints,
                                     cudaMemcpyDeviceToHost, F->s_comp));
     }
-    for (size_t c = 0; c < F->chunks.size(); ++c) {
-        const Chunk &ch = F->chunks[c];
+    for (size_t c = 0; c < F->chunks_inv.size(); ++c) {
+        const Chunk &ch = F->chunks_inv[c];
         if ((rc = copy_interleaved(*F, ch, N, F->d_a.p, state, cudaMemcpyHostToDevice, F->s_in))) return rc;
         SZB_CUDA_OK(cudaEventRecord(F->ev_in[c], F->s_in));
         SZB_CUDA_OK(cudaStreamWaitEvent(F->s_comp, F->ev_in[c], 0));
