@@ -117,6 +117,7 @@ struct PSmem {
     unsigned char *tblk;   // [76]
     double *drow;     // [2][3][LDMAX]   operator rows of the block assembled in iteration parity p
     double *refcol;   // [2][32]         reference-profile column for its new coefficient point
+    double *sred;     // [8]             solver warp: the four reduced dot products of a chunk
 };
 
 template <class W>
@@ -126,7 +127,7 @@ __host__ __device__ inline size_t pipe_smem_bytes(int N)
                                + MAXTERMS + 2 * (size_t) N + W::NB * W::CH * W::KL);
     b += 8 * W::NB + 4 * (2 * P + 32) + 2 * (size_t) N + MAXTERMS + 80;
     b = (b + 15) & ~(size_t) 15;
-    b += 8 * (2 * 3 * W::LDMAX + 2 * 32);
+    b += 8 * (2 * 3 * W::LDMAX + 2 * 32 + 8);
     return b;
 }
 
@@ -152,7 +153,8 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
     S.tblk = q; q += 80;
     q = raw + (((size_t) (q - raw) + 15) & ~(size_t) 15);
     S.drow = reinterpret_cast<double *>(q); q += 8 * 2 * 3 * W::LDMAX;
-    S.refcol = reinterpret_cast<double *>(q);
+    S.refcol = reinterpret_cast<double *>(q); q += 8 * 2 * 32;
+    S.sred = reinterpret_cast<double *>(q);
     return S;
 }
 
@@ -381,6 +383,71 @@ invert_pipe_kernel(const PipeArgs A)
                     mbar_wait(S.mbar + slot, parity);
                     const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
                     const cplx *Lc = S.lring + (size_t) slot * CH * KL;
+                    // Four columns at a time when none of them carries an interchange: the parts of
+                    // their four dot products that involve already final x (rows past the chunk) are
+                    // formed together and reduced with one packed butterfly (8 doubles -> 4 -> 2 -> 1
+                    // per lane), then lane 0 finishes the 4 x 4 triangle.  Otherwise column by column.
+                    bool plain = CH == 4 && jhi - jlo + 1 == CH;
+                    if (plain)
+                        plain = (jpv[jlo] | jpv[jlo + 1] | jpv[jlo + 2] | jpv[jlo + 3]) == 0;
+                    if (plain) {
+                        double v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.0;
+                        for (int t = lane; t < KL; t += 32) {
+                            const int pz = jhi + 1 + t;
+                            if (pz <= N - 1) {
+                                const cplx xv = x[pz];
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) {
+                                    const int i = pz - (jlo + qq);                 // >= 1
+                                    if (i <= KL) {
+                                        cplx sq(v[2 * qq], v[2 * qq + 1]);
+                                        addmul(sq, Lc[qq * KL + i - 1], xv);
+                                        v[2 * qq] = sq.x; v[2 * qq + 1] = sq.y;
+                                    }
+                                }
+                            }
+                        }
+                        double w4[4], w2[2], w1;
+                        {
+                            const bool up = lane & 16;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const double send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+                                w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+                        }
+                        {
+                            const bool up = lane & 8;
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) {
+                                const double send = up ? w4[i] : w4[i + 2], keep = up ? w4[i + 2] : w4[i];
+                                w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+                        }
+                        {
+                            const bool up = lane & 4;
+                            const double send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                        // lane 4 i holds component i: (s0.x, s0.y, s1.x, ..., s3.y)
+                        if ((lane & 3) == 0) S.sred[lane >> 2] = w1;
+                        __syncwarp();
+                        if (lane == 0) {
+                            const cplx s0(S.sred[0], S.sred[1]), s1(S.sred[2], S.sred[3]);
+                            const cplx s2(S.sred[4], S.sred[5]), s3(S.sred[6], S.sred[7]);
+                            const cplx *L0 = Lc, *L1 = Lc + KL, *L2 = Lc + 2 * KL;
+                            const cplx x3 = x[jlo + 3] - s3;
+                            cplx x2 = x[jlo + 2] - s2; submul(x2, L2[0], x3);
+                            cplx x1 = x[jlo + 1] - s1; submul(x1, L1[0], x2); submul(x1, L1[1], x3);
+                            cplx x0 = x[jlo] - s0; submul(x0, L0[0], x1); submul(x0, L0[1], x2); submul(x0, L0[2], x3);
+                            x[jlo + 3] = x3; x[jlo + 2] = x2; x[jlo + 1] = x1; x[jlo] = x0;
+                        }
+                        __syncwarp();
+                    } else
                     for (int j = jhi; j >= jlo; --j) {
                         const int lm = min(KL, N - 1 - j);
                         const cplx *Lj = Lc + (size_t) (j - jlo) * KL;
