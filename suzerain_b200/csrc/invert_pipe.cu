@@ -120,41 +120,56 @@ struct PSmem {
     double *sred;     // [8]             solver warp: the four reduced dot products of a chunk
 };
 
+// Everything whose size does not depend on N comes first, so that its shared-memory
+// addresses are compile-time offsets; the two N-sized arrays (v, ipiv) close the block.
 template <class W>
-__host__ __device__ inline size_t pipe_smem_bytes(int N)
-{
-    size_t b = sizeof(cplx) * ((size_t) W::NS * W::CW + 2 * W::NS * P + 2 * 2 * 8 + 2 * P * W::CW + W::CR * W::NCOEF
-                               + MAXTERMS + 2 * (size_t) N + W::NB * W::CH * W::KL);
-    b += 8 * W::NB + 4 * (2 * P + 32) + 2 * (size_t) N + MAXTERMS + 80;
-    b = (b + 15) & ~(size_t) 15;
-    b += 8 * (2 * 3 * W::LDMAX + 2 * 32 + 8);
-    return b;
-}
+struct PipeLayout {
+    static constexpr size_t C = sizeof(cplx);
+    static constexpr size_t win = 0;
+    static constexpr size_t lp = win + C * W::NS * W::CW;
+    static constexpr size_t rec = lp + C * 2 * W::NS * P;
+    static constexpr size_t stage = rec + C * 2 * 2 * 8;
+    static constexpr size_t coef = stage + C * 2 * P * W::CW;
+    static constexpr size_t alpha = coef + C * W::CR * W::NCOEF;
+    static constexpr size_t lring = alpha + C * MAXTERMS;
+    static constexpr size_t drow = lring + C * W::NB * W::CH * W::KL;
+    static constexpr size_t refcol = drow + 8 * 2 * 3 * W::LDMAX;
+    static constexpr size_t sred = refcol + 8 * 2 * 32;
+    static constexpr size_t mbar = sred + 8 * 8;
+    static constexpr size_t pivslot = mbar + 8 * W::NB;
+    static constexpr size_t misc = pivslot + 4 * 2 * P;
+    static constexpr size_t tref = misc + 4 * 32;
+    static constexpr size_t tblk = tref + MAXTERMS;
+    static constexpr size_t v = (tblk + 80 + 15) / 16 * 16;
+    __host__ __device__ static constexpr size_t ipiv(int N) { return v + C * 2 * (size_t) N; }
+    __host__ __device__ static constexpr size_t bytes(int N) { return (ipiv(N) + 2 * (size_t) N + 15) / 16 * 16; }
+};
+
+template <class W>
+__host__ __device__ inline size_t pipe_smem_bytes(int N) { return PipeLayout<W>::bytes(N); }
 
 template <class W>
 __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
 {
+    using Y = PipeLayout<W>;
     PSmem<W> S;
-    cplx *p = reinterpret_cast<cplx *>(raw);
-    S.win = p;   p += W::NS * W::CW;
-    S.lp = p;    p += 2 * W::NS * P;
-    S.rec = p;   p += 2 * 2 * 8;
-    S.stage = p; p += 2 * P * W::CW;
-    S.coef = p;  p += W::CR * W::NCOEF;
-    S.alpha = p; p += MAXTERMS;
-    S.v = p;     p += 2 * (size_t) N;
-    S.lring = p; p += W::NB * W::CH * W::KL;
-    unsigned char *q = reinterpret_cast<unsigned char *>(p);
-    S.mbar = reinterpret_cast<unsigned long long *>(q); q += 8 * W::NB;
-    S.pivslot = reinterpret_cast<int *>(q); q += 4 * 2 * P;
-    S.misc = reinterpret_cast<int *>(q); q += 4 * 32;
-    S.ipiv = q; q += 2 * (size_t) N;
-    S.tref = q; q += MAXTERMS;
-    S.tblk = q; q += 80;
-    q = raw + (((size_t) (q - raw) + 15) & ~(size_t) 15);
-    S.drow = reinterpret_cast<double *>(q); q += 8 * 2 * 3 * W::LDMAX;
-    S.refcol = reinterpret_cast<double *>(q); q += 8 * 2 * 32;
-    S.sred = reinterpret_cast<double *>(q);
+    S.win = reinterpret_cast<cplx *>(raw + Y::win);
+    S.lp = reinterpret_cast<cplx *>(raw + Y::lp);
+    S.rec = reinterpret_cast<cplx *>(raw + Y::rec);
+    S.stage = reinterpret_cast<cplx *>(raw + Y::stage);
+    S.coef = reinterpret_cast<cplx *>(raw + Y::coef);
+    S.alpha = reinterpret_cast<cplx *>(raw + Y::alpha);
+    S.lring = reinterpret_cast<cplx *>(raw + Y::lring);
+    S.drow = reinterpret_cast<double *>(raw + Y::drow);
+    S.refcol = reinterpret_cast<double *>(raw + Y::refcol);
+    S.sred = reinterpret_cast<double *>(raw + Y::sred);
+    S.mbar = reinterpret_cast<unsigned long long *>(raw + Y::mbar);
+    S.pivslot = reinterpret_cast<int *>(raw + Y::pivslot);
+    S.misc = reinterpret_cast<int *>(raw + Y::misc);
+    S.tref = raw + Y::tref;
+    S.tblk = raw + Y::tblk;
+    S.v = reinterpret_cast<cplx *>(raw + Y::v);
+    S.ipiv = raw + Y::ipiv(N);
     return S;
 }
 
