@@ -305,7 +305,7 @@ __device__ __noinline__ double2 exact_recip(double x, double y)
 // Each ends with a CTA barrier; afterwards the panel warp loads block t and factors it
 // while the update warps do the rest of U(t-1).
 template <class W, class SM>
-__device__ __forceinline__ void lookahead_phases(const SM &S, int j, int jc, int par, int tid)
+__device__ __forceinline__ void lookahead_phases(const SM &S, unsigned sbase, int j, int jc, int par, int tid)
 {
     constexpr int NS = W::NS, CW = W::CW, NT = W::NT;
     const int *opiv = S.pivslot + (par ^ 1) * P;
@@ -335,7 +335,7 @@ __device__ __forceinline__ void lookahead_phases(const SM &S, int j, int jc, int
         cplx w = S.win[(size_t) s * CW + ccs];
 #pragma unroll
         for (int i = 0; i < P; ++i) submul(w, lpo[s * P + i], S.win[(size_t) ps[i] * CW + ccs]);
-        st_shared_if(S.win + (size_t) s * CW + ccs, w, !((omask >> s) & 1));
+        sts_if(sbase + (unsigned) PipeLayout<W>::win + 16u * (unsigned) (s * CW + ccs), w, !((omask >> s) & 1));
     }
     bar_sync_n<1>(NT);
 }
@@ -351,7 +351,11 @@ invert_pipe_kernel(const PipeArgs A)
     // logical thread index: warps are dealt to the four SM sub-partitions round-robin, so the
     // roles are permuted to keep the latency-critical panel warps away from the FP64-heavy
     // update warps (see PipeCfg::logical_warp)
-    const int tid = W::logical_warp(threadIdx.x >> 5) * 32 + (threadIdx.x & 31);
+    int tid = W::logical_warp(threadIdx.x >> 5) * 32 + (threadIdx.x & 31);
+    pin(tid);
+    using Y = PipeLayout<W>;
+    unsigned sbase = smem_u32(smem_raw);                          // shared-window address of the block
+    pin(sbase);
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
     constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_PP = 7;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
@@ -570,8 +574,8 @@ invert_pipe_kernel(const PipeArgs A)
             int lg = slot < RW ? slot : INT_MAX;
             int pk = slot < NS ? P : -1;
             cplx a[P];
-            unsigned rec_sa = smem_u32(S.rec), sv_sa = smem_u32(sv), jpv_sa = smem_u32(jpv);
-            unsigned xmh_sa = smem_u32(S.misc + 12);
+            unsigned rec_sa = sbase + (unsigned) Y::rec, sv_sa = sbase + (unsigned) (Y::v + sizeof(cplx) * (size_t) buf * N);
+            unsigned jpv_sa = sbase + (unsigned) (Y::ipiv(N) + (size_t) buf * N), xmh_sa = sbase + (unsigned) Y::misc + 48;
             pin(rec_sa); pin(sv_sa); pin(jpv_sa); pin(xmh_sa);
             // (b) lane predicates as pinned registers (the compiler otherwise re-reads SR_TID)
             int is_lead = tid == NTU + W::NTA, is_rhs = slot == RW, is_l0 = lane == 0;
@@ -581,7 +585,7 @@ invert_pipe_kernel(const PipeArgs A)
             for (int j = 0; j < N; j += P, par ^= 1) {
                 // block t of every row: entering rows from the stage, the others from the
                 // window once panel t-1 has been applied to it
-                if (j > 0) lookahead_phases<W>(S, j, jc, par, tid);
+                if (j > 0) lookahead_phases<W>(S, sbase, j, jc, par, tid);
                 PROF_MARK(0);
                 {
                     const cplx *stg = S.stage + (size_t) (par ^ 1) * P * CW;
@@ -597,8 +601,8 @@ invert_pipe_kernel(const PipeArgs A)
                     if (ret) { lg = j - P + RW + pk; if (lg >= N) lg = INT_MAX; pk = P; }
                 }
                 PROF_MARK(1);
-                unsigned lp_sa = smem_u32(S.lp + (size_t) par * NS * P + slot * P);
-                unsigned piv_sa = smem_u32(S.pivslot + par * P);
+                unsigned lp_sa = sbase + (unsigned) (Y::lp + sizeof(cplx) * ((size_t) par * NS * P + slot * P));
+                unsigned piv_sa = sbase + (unsigned) (Y::pivslot + 4 * par * P);
                 pin(lp_sa); pin(piv_sa);
                 cplx *Lcol = Lg + (size_t) j * KL - (j + 1);                // L(lg, col) at Lcol[lg]
                 // Every lane inverts its candidate of the coming column while the current one is being
@@ -743,7 +747,7 @@ invert_pipe_kernel(const PipeArgs A)
             PROF_DECL
             for (int j = 0; j < N; j += P, par ^= 1) {
                 if (j > 0) {
-                    lookahead_phases<W>(S, j, jc, par, tid);
+                    lookahead_phases<W>(S, sbase, j, jc, par, tid);
                     PROF_MARK(0);
                     const int jo = j - P;                         // previous panel
                     const int *opiv = S.pivslot + (par ^ 1) * P;
@@ -786,8 +790,8 @@ invert_pipe_kernel(const PipeArgs A)
                                     }
 #pragma unroll
                                     for (int m = 0; m < P; ++m) submul(w, l[m], u[m]);
-                                    st_shared_if(S.win + (size_t) min(s, NS - 1) * CW + ccs, w,
-                                                 s < NS && !((omask >> s) & 1));
+                                    sts_if(sbase + (unsigned) Y::win + 16u * (unsigned) (min(s, NS - 1) * CW + ccs), w,
+                                           s < NS && !((omask >> s) & 1));
                                 }
                             }
                         }
@@ -832,7 +836,7 @@ invert_pipe_kernel(const PipeArgs A)
             const int ta = tid - NTU;
             int jc = 0, par = 0;
             for (int j = 0; j < N; j += P, par ^= 1) {
-                if (j > 0) lookahead_phases<W>(S, j, jc, par, tid);
+                if (j > 0) lookahead_phases<W>(S, sbase, j, jc, par, tid);
                 // ---- A(t): the block entering after this panel, from the staged operator rows
                 // and profile column; then stage the next iteration's ----
                 const int yI = (j + RW) / 5;
