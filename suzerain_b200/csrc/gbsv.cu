@@ -484,6 +484,17 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
                                         pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
         if (rc <= 0) return rc;
     }
+    // zcgbsvx with its default eps tolerance: refinement around the fused kernel (the factors
+    // are recomputed per step instead of being stored); SZB_INVERT=v1 keeps the generic kernel
+    if (spec->method == SZB_SOLVER_ZCGBSVX && nextra == 0 && spec->tolsc == 0.0 && spec->aiter >= 1) {
+        static const bool generic = [] { const char *e = std::getenv("SZB_INVERT"); return e && e[0] == 'v' && e[1] == '1'; }();
+        if (!generic) {
+            const int rc = invert_refined_dispatch(op, spec->aiter, spec->diter, phi, npencil, d_km, d_kn, d_index,
+                                                   reinterpret_cast<cplx *>(d_state), field_stride, pencil_stride,
+                                                   d_ipiv, d_info, d_iters, (cudaStream_t) stream);
+            if (rc <= 0) return rc;
+        }
+    }
 
     InvertArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);

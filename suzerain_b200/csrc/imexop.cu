@@ -263,6 +263,7 @@ int szb_imexop_create(const szb_bsplineop *w, szb_imexop **out)
     op->A = szb_bsmbsm_construct(5, w->n, w->max_kl, w->max_ku);
     op->d_D = nullptr; op->d_refs = nullptr; op->d_terms = nullptr;
     op->d_work = nullptr; op->work_bytes = 0; op->work_slots = 0; op->field_ctx = nullptr;
+    op->d_refine = nullptr; op->refine_bytes = 0;
     op->have_a = op->have_b = op->have_c = false;
     std::memset(&op->iso, 0, sizeof(op->iso));
     op->iso.enforce_lower = 1; op->iso.enforce_upper = 1;
@@ -302,7 +303,7 @@ void szb_imexop_destroy(szb_imexop *op)
 {
     if (!op) return;
     if (op->field_ctx) szb::field_ctx_free(op->field_ctx);
-    cudaFree(op->d_D); cudaFree(op->d_refs); cudaFree(op->d_terms); cudaFree(op->d_work);
+    cudaFree(op->d_D); cudaFree(op->d_refs); cudaFree(op->d_terms); cudaFree(op->d_work); cudaFree(op->d_refine);
     delete op;
 }
 

@@ -32,7 +32,11 @@ int invert_window_dispatch(const szb_imexop *op, const double phi[2], int npenci
 int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                         int *d_iters, cudaStream_t stream);
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
+int invert_refined_dispatch(const szb_imexop *op, int aiter, int dmax, const double phi[2], int npencil,
+                            const double *d_km, const double *d_kn, const int *d_index,
+                            cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                            int *d_iters, cudaStream_t stream);
 int invert_blocked_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
@@ -96,5 +100,7 @@ struct szb_imexop {
     mutable size_t work_bytes;
     mutable int    work_slots;
     mutable void  *field_ctx;          // cached whole-field plan (capi.cu)
+    mutable void  *d_refine;           // workspace of the refined fused invert (invert_pipe.cu)
+    mutable size_t refine_bytes;
     int sm_count;
 };

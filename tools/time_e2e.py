@@ -8,7 +8,7 @@ import suzerain_b200 as sz
 import bench
 wl = bench.Workload("channel_192x96x192")
 op = wl.make_imexop()
-spec = sz.SolverSpec(method="zgbsv")
+spec = sz.SolverSpec(method=(sys.argv[1] if len(sys.argv) > 1 else "zgbsv"))
 OH = sz.OperatorHybridIsothermal(op, wl.grid, spec)
 h = wl.host_state()
 hin = torch.from_numpy(h).pin_memory(); hout = torch.zeros((5, wl.npencil, wl.Ny), dtype=torch.complex128).pin_memory()
