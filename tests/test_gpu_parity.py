@@ -81,6 +81,11 @@ def test_invert_matches_oracle(dev, request, casename, solver):
     assert np.all(got["info"] == 0)
     assert np.array_equal(got["ipiv"], want["ipiv"]), "pivot choices differ"
     assert pc.relmax(got["x"], want["x"]) <= TOL
+    if solver == "zcgbsvx":
+        # refinement counter as the reference reports it (dsgbsvx.def:169-170, 256-290): the stopping
+        # tests compare residual norms at the rounding level, so allow a step of slack on a few pencils
+        d = np.abs(got["iters"].astype(int) - want["iters"].astype(int))
+        assert d.max() <= 1 and (d != 0).mean() <= 0.2, (got["iters"], want["iters"])
 
 
 def test_invert_extra_rhs(dev, tiny):
