@@ -393,7 +393,7 @@ def run_b200(args):
         "roofline": {"kernel": "invert (assemble + factor + solve, fused)", "bound": "hbm",
                      "achieved": inv_gbs, "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                     "unit": "GB/s", "frac": inv_gbs / peak, "traffic": tr("invert_blocked"),
+                     "unit": "GB/s", "frac": inv_gbs / peak, "traffic": tr("invert_pipe"),
                      "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch)",
                      "ms_per_launch": inv_ms, "algorithmic_bytes_per_launch": inv_bytes,
                      "fp64_gflops_upper": lu_flop * wl.nactive / (inv_ms * 1e-3) / 1e9},
