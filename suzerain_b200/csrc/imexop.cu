@@ -67,11 +67,11 @@ static void build_terms(const szb_rholut_imexop_scenario &s, TermTable &tt)
 // ---------------------------------------------------------------------------
 // accumulate: out <- (M + phi L) in + beta out, one CTA per pencil.
 //
-// Shared memory holds the five input pencils (5*n complex), the 15 banded products
-// and the per-term coefficients alpha_t = phi * sc_t * wave_t(km, kn):
-//   P[d][j](y) = sum_r D^(d)[y, y - ku + r] * in_j[y - ku + r]      one thread per (j, y)
+// Shared memory holds the five input pencils (zero halo) and the per-term coefficients
+// alpha_t = phi * sc_t * wave_t(km, kn); one thread per collocation point y:
+//   P[d][j](y) = sum_r D^(d)[y, y - ku + r] * in_j[y - ku + r]      fifteen products in registers
 //   out_i(y)   = beta out_i + sum_{blocks (i,j,d)} (sum_t alpha_t ref_t[y]) P[d][j]
-//                + P[M][i]                                (mass added last)   one thread per (i, y)
+//                + P[M][i]                                (mass added last)
 // The block structure of each row is unrolled at compile time from rholut_terms.def.
 // HBM traffic is the algorithmic minimum: every state element is read once and written
 // once (plus one read of the output when beta != 0); operators and profiles stay in L1/L2.
@@ -89,15 +89,16 @@ struct AccumulateArgs {
     double a[25], b[25], c[25];
 };
 
-// One output row of (M + phi L) at collocation point y, statically specialised on the
-// equation ROW: only that row's terms of rholut_terms.def survive constant folding.
+// One output row of phi L at collocation point y, statically specialised on the equation
+// ROW: only that row's terms of rholut_terms.def survive constant folding.  Pm[op][col] are
+// this point's fifteen banded products, held in registers.
 template <int ROW>
 __device__ __forceinline__ cplx accumulate_row(const double *refs, int n, int y, const cplx *s_alpha,
-                                               const cplx *s_P)
+                                               const cplx (&Pm)[3][5])
 {
     cplx acc(0.0, 0.0), c(0.0, 0.0);
     int t = 0, cur = -1, ccol = 0, cop = 0;
-#define SZB_FLUSH() do { if (cur >= 0) acc += c * s_P[(size_t) (cop * 5 + ccol) * n + y]; } while (0)
+#define SZB_FLUSH() do { if (cur >= 0) acc += c * Pm[cop][ccol]; } while (0)
 #define SZB_TERM(row, col, op, ref, wave, scen)                                  \
     if (szb::row == ROW) {                                                       \
         if ((szb::col) * 3 + szb::op != cur) {                                   \
@@ -115,17 +116,19 @@ __device__ __forceinline__ cplx accumulate_row(const double *refs, int n, int y,
     return acc;
 }
 
-// Work is split twice over the CTA: first one thread per (field j, point y) forms the
-// three banded products D^(0..2) in_j at y into shared memory, then one thread per
-// (equation i, point y) combines them with the reference profiles.
-__global__ void __launch_bounds__(256)
+// One CTA per pencil, one thread per collocation point y.  The thread forms the fifteen
+// banded products D^(0..2) in_j at y in registers (every operator entry is loaded once and
+// used for the five fields; the fields sit in shared memory with a zero halo of ku / kl
+// points, so there are no bounds tests) and combines them into the five output rows
+// straight away: no second pass, no products in shared memory.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 accumulate_kernel(const AccumulateArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = A.n;
-    cplx *s_in    = reinterpret_cast<cplx *>(smem_raw);            // [5][n]
-    cplx *s_P     = s_in + 5 * n;                                  // [3][5][n]
-    cplx *s_alpha = s_P + 15 * n;                                  // [MAXTERMS]
+    const int n = A.n, ku = A.ku, kl = A.kl, np = n + ku + kl;
+    cplx *s_in    = reinterpret_cast<cplx *>(smem_raw);            // [5][ku + n + kl]
+    cplx *s_alpha = s_in + 5 * np;                                 // [MAXTERMS]
     cplx *s_top   = s_alpha + MAXTERMS;                            // [5] phi L in at the upper boundary
 
     const int p = blockIdx.x;
@@ -134,52 +137,54 @@ accumulate_kernel(const AccumulateArgs A)
     const cplx *in = A.in + slot * A.in_ps;
     cplx *out = A.out + slot * A.out_ps;
 
-    for (int e = threadIdx.x; e < 5 * n; e += blockDim.x) {
-        const int f = e / n, y = e - f * n;
-        s_in[e] = in[(size_t) f * A.in_fs + y];
+    for (int e = threadIdx.x; e < 5 * np; e += blockDim.x) {
+        const int f = e / np, yy = e - f * np - ku;
+        s_in[e] = (yy >= 0 && yy < n) ? in[(size_t) f * A.in_fs + yy] : cplx(0.0, 0.0);
     }
     const int nterms = A.terms->nterms;
     for (int t = threadIdx.x; t < nterms; t += blockDim.x)
         s_alpha[t] = A.phi * (wave_factor(A.terms->wave[t], km, kn) * A.terms->sc[t]);
     __syncthreads();
 
-    // ---- banded products: P[d][j](y) = sum_r D^(d)[y, y-ku+r] in_j[y-ku+r] ----
-    for (int e = threadIdx.x; e < 5 * n; e += blockDim.x) {
-        const int j = e / n, y = e - j * n;
-        cplx P0(0.0, 0.0), P1(0.0, 0.0), P2(0.0, 0.0);
-        const int r0 = max(0, A.ku - y), r1 = min(A.ld, n - y + A.ku);
-        const cplx *x = s_in + j * n + (y - A.ku);
-        const double *D0 = A.D + y, *D1 = D0 + (size_t) A.ld * n, *D2 = D1 + (size_t) A.ld * n;
-        for (int r = r0; r < r1; ++r) {
-            const cplx v = x[r];
-            addmul(P0, v, __ldg(D0 + (size_t) r * n));
-            addmul(P1, v, __ldg(D1 + (size_t) r * n));
-            addmul(P2, v, __ldg(D2 + (size_t) r * n));
-        }
-        s_P[(size_t) (0 * 5 + j) * n + y] = P0;
-        s_P[(size_t) (1 * 5 + j) * n + y] = P1;
-        s_P[(size_t) (2 * 5 + j) * n + y] = P2;
-    }
-    __syncthreads();
-
-    // ---- rows: out_i = beta out_i + phi L in (+ NRBC) + M in_i, mass added last ----
     const bool beta_zero = is_zero(A.beta);
     const bool nrbc = A.nrbc != 0;
-    for (int e = threadIdx.x; e < 5 * n; e += blockDim.x) {
-        const int i = e / n, y = e - i * n;
-        cplx phiL;
-        switch (i) {
-        case 0:  phiL = accumulate_row<0>(A.refs, n, y, s_alpha, s_P); break;
-        case 1:  phiL = accumulate_row<1>(A.refs, n, y, s_alpha, s_P); break;
-        case 2:  phiL = accumulate_row<2>(A.refs, n, y, s_alpha, s_P); break;
-        case 3:  phiL = accumulate_row<3>(A.refs, n, y, s_alpha, s_P); break;
-        default: phiL = accumulate_row<4>(A.refs, n, y, s_alpha, s_P); break;
+    for (int y = threadIdx.x; y < n; y += blockDim.x) {
+        // ---- banded products: P[d][j](y) = sum_r D^(d)[y, y-ku+r] in_j[y-ku+r] ----
+        cplx Pm[3][5];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) Pm[d][j] = cplx(0.0, 0.0);
+        const double *D0 = A.D + y;
+        const size_t ds = (size_t) A.ld * n;
+#pragma unroll 2
+        for (int r = 0; r < A.ld; ++r) {
+            // entries outside the matrix are zero in the band storage and meet the zero halo
+            const double d0 = __ldg(D0 + (size_t) r * n), d1 = __ldg(D0 + ds + (size_t) r * n),
+                         d2 = __ldg(D0 + 2 * ds + (size_t) r * n);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const cplx v = s_in[j * np + y + r];
+                addmul(Pm[0][j], v, d0);
+                addmul(Pm[1][j], v, d1);
+                addmul(Pm[2][j], v, d2);
+            }
         }
-        cplx *o = out + (size_t) i * A.out_fs + y;
-        cplx acc = beta_zero ? phiL : A.beta * (*o) + phiL;
-        acc += s_P[(size_t) i * n + y];                              // M in_i (d = 0, j = i)
-        if (nrbc && y == n - 1) s_top[i] = phiL;
-        *o = acc;
+        // ---- rows: out_i = beta out_i + phi L in (+ NRBC) + M in_i, mass added last ----
+        cplx phiL[5];
+        phiL[0] = accumulate_row<0>(A.refs, n, y, s_alpha, Pm);
+        phiL[1] = accumulate_row<1>(A.refs, n, y, s_alpha, Pm);
+        phiL[2] = accumulate_row<2>(A.refs, n, y, s_alpha, Pm);
+        phiL[3] = accumulate_row<3>(A.refs, n, y, s_alpha, Pm);
+        phiL[4] = accumulate_row<4>(A.refs, n, y, s_alpha, Pm);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            cplx *o = out + (size_t) i * A.out_fs + y;
+            cplx acc = beta_zero ? phiL[i] : A.beta * (*o) + phiL[i];
+            acc += Pm[0][i];                                         // M in_i (d = 0, j = i)
+            if (nrbc && y == n - 1) s_top[i] = phiL[i];
+            *o = acc;
+        }
     }
     if (nrbc) {
         // upper-boundary correction (rholut_imexop.c:510-545):
@@ -191,12 +196,12 @@ accumulate_kernel(const AccumulateArgs A)
             const cplx ikmphi = cplx(0.0, km) * A.phi, iknphi = cplx(0.0, kn) * A.phi;
             if (A.nrbc & 1) {
                 cplx s(0.0, 0.0);
-                for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.a[i + 5 * j];
+                for (int j = 0; j < 5; ++j) s += s_in[j * np + ku + (n - 1)] * A.a[i + 5 * j];
                 tt -= ikmphi * s;
             }
             if (A.nrbc & 2) {
                 cplx s(0.0, 0.0);
-                for (int j = 0; j < 5; ++j) s += s_in[j * n + (n - 1)] * A.b[i + 5 * j];
+                for (int j = 0; j < 5; ++j) s += s_in[j * np + ku + (n - 1)] * A.b[i + 5 * j];
                 tt -= iknphi * s;
             }
             if (A.nrbc & 4) {
@@ -395,11 +400,19 @@ int szb_imexop_accumulate_batch(const szb_imexop *op, const double phi[2],
     std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
     std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
     std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
-    const size_t smem = sizeof(cplx) * (20 * (size_t) op->n + MAXTERMS + 8);
+    const size_t smem = sizeof(cplx) * (5 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
     if (smem > 227 * 1024) return -1;
-    if (smem > 48 * 1024)
-        SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    accumulate_kernel<<<npencil, 256, smem, (cudaStream_t) stream>>>(A);
+    int threads = (op->n + 31) / 32 * 32;
+    if (threads > 512) threads = 512;
+    if (threads <= 128) {
+        if (smem > 48 * 1024)
+            SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        accumulate_kernel<128, 4><<<npencil, threads, smem, (cudaStream_t) stream>>>(A);
+    } else {
+        if (smem > 48 * 1024)
+            SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        accumulate_kernel<512, 1><<<npencil, threads, smem, (cudaStream_t) stream>>>(A);
+    }
     count_launch();
     SZB_CUDA_OK(cudaGetLastError());
     return 0;
