@@ -14,7 +14,9 @@
 
 #include "szb_internal.hpp"
 #include "cplx.cuh"
+#include <algorithm>
 #include "kernels.cuh"
+#include "invert_common.cuh"
 
 namespace szb {
 
@@ -87,6 +89,7 @@ struct AccumulateArgs {
     cplx       *out; size_t out_fs, out_ps;
     int nrbc;               // bit0 a, bit1 b, bit2 c
     double a[25], b[25], c[25];
+    int npencil;
 };
 
 // One output row of phi L at collocation point y, statically specialised on the equation
@@ -126,24 +129,42 @@ __global__ void __launch_bounds__(MAXT, MINB)
 accumulate_kernel(const AccumulateArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
     const int n = A.n, ku = A.ku, kl = A.kl, np = n + ku + kl;
-    cplx *s_in    = reinterpret_cast<cplx *>(smem_raw);            // [5][ku + n + kl]
-    cplx *s_alpha = s_in + 5 * np;                                 // [MAXTERMS]
+    cplx *s_inbuf = reinterpret_cast<cplx *>(smem_raw);            // [2][5][ku + n + kl]
+    cplx *s_alpha = s_inbuf + 2 * 5 * np;                          // [MAXTERMS]
     cplx *s_top   = s_alpha + MAXTERMS;                            // [5] phi L in at the upper boundary
 
-    const int p = blockIdx.x;
+    // Persistent CTA: the five field pencils of the next (kx,kz) arrive by TMA bulk copies
+    // (one per field, interior of a zero-halo buffer) while the current one is computed.
+    for (int e = threadIdx.x; e < 2 * 5 * np; e += blockDim.x) s_inbuf[e] = cplx(0.0, 0.0);
+    if (threadIdx.x == 0) {
+        fused::mbar_init(&s_mbar[0], 1); fused::mbar_init(&s_mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned bytes = (unsigned) (n * sizeof(cplx));
+    auto fetch = [&](int p, int stage) {
+        const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
+        const cplx *src = A.in + slot * A.in_ps;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fused::mbar_expect_tx(&s_mbar[stage], 5 * bytes);
+        for (int f = 0; f < 5; ++f)
+            fused::tma_bulk_g2s(s_inbuf + (stage * 5 + f) * np + ku, src + (size_t) f * A.in_fs, bytes, &s_mbar[stage]);
+    };
+    if (threadIdx.x == 0 && (int) blockIdx.x < A.npencil) fetch(blockIdx.x, 0);
+    const int nterms = A.terms->nterms;
+    int it = 0;
+    for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const cplx *s_in = s_inbuf + stage * 5 * np;
     const double km = A.km[p], kn = A.kn[p];
     const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
-    const cplx *in = A.in + slot * A.in_ps;
     cplx *out = A.out + slot * A.out_ps;
-
-    for (int e = threadIdx.x; e < 5 * np; e += blockDim.x) {
-        const int f = e / np, yy = e - f * np - ku;
-        s_in[e] = (yy >= 0 && yy < n) ? in[(size_t) f * A.in_fs + yy] : cplx(0.0, 0.0);
-    }
-    const int nterms = A.terms->nterms;
+    if (threadIdx.x == 0 && p + (int) gridDim.x < A.npencil) fetch(p + gridDim.x, stage ^ 1);
     for (int t = threadIdx.x; t < nterms; t += blockDim.x)
         s_alpha[t] = A.phi * (wave_factor(A.terms->wave[t], km, kn) * A.terms->sc[t]);
+    fused::mbar_wait(&s_mbar[stage], (it >> 1) & 1);
     __syncthreads();
 
     const bool beta_zero = is_zero(A.beta);
@@ -212,6 +233,8 @@ accumulate_kernel(const AccumulateArgs A)
             cplx *o = out + (size_t) i * A.out_fs + (n - 1);
             *o = *o + tt;
         }
+    }
+    __syncthreads();          // alpha, s_top and this stage's buffer are free again
     }
 }
 
@@ -400,18 +423,19 @@ int szb_imexop_accumulate_batch(const szb_imexop *op, const double phi[2],
     std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
     std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
     std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
-    const size_t smem = sizeof(cplx) * (5 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
+    A.npencil = npencil;
+    const size_t smem = sizeof(cplx) * (10 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
     if (smem > 227 * 1024) return -1;
     int threads = (op->n + 31) / 32 * 32;
     if (threads > 512) threads = 512;
     if (threads <= 128) {
         if (smem > 48 * 1024)
             SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        accumulate_kernel<128, 4><<<npencil, threads, smem, (cudaStream_t) stream>>>(A);
+        accumulate_kernel<128, 4><<<std::min(npencil, 5 * op->sm_count), threads, smem, (cudaStream_t) stream>>>(A);
     } else {
         if (smem > 48 * 1024)
             SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        accumulate_kernel<512, 1><<<npencil, threads, smem, (cudaStream_t) stream>>>(A);
+        accumulate_kernel<512, 1><<<std::min(npencil, 2 * op->sm_count), threads, smem, (cudaStream_t) stream>>>(A);
     }
     count_launch();
     SZB_CUDA_OK(cudaGetLastError());
