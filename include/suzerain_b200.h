@@ -299,6 +299,18 @@ int szb_wavegrid_nactive (const szb_wavegrid *g);
 int szb_wavegrid_wavenumbers(const szb_wavegrid *g, double *km, double *kn,
                              int *active);
 
+/* Wave-space differentiation of Ny-long pencils stored [kz][kx][y] on the device:
+ *   apply:      x <- alpha (i kx)^dxcnt (i kz)^dzcnt x
+ *   accumulate: y <- alpha (i kx)^dxcnt (i kz)^dzcnt x + beta y
+ * with dealiased and Nyquist modes zeroed (scaled by beta).  Replace
+ * suzerain_diffwave_apply / suzerain_diffwave_accumulate (suzerain/diffwave.c:65-129,
+ * 131-198; the wave-space half of the nonlinear operator, navier_stokes.hpp:227-331). */
+int szb_diffwave_apply_batch(int dxcnt, int dzcnt, const double alpha[2],
+        szb_complex *d_x, const szb_wavegrid *g, int Ny, void *stream);
+int szb_diffwave_accumulate_batch(int dxcnt, int dzcnt, const double alpha[2],
+        const szb_complex *d_x, const double beta[2], szb_complex *d_y,
+        const szb_wavegrid *g, int Ny, void *stream);
+
 /* `state` is the interleaved state [5][Ny][Nx_loc][Nz_loc] with strides
  * (Ny, 1, 5*Ny, 5*Ny*Nx_loc) (suzerain/storage.hpp:235-236). */
 int szb_operator_apply_mass_plus_scaled_operator(const szb_imexop *op,

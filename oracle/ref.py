@@ -189,6 +189,18 @@ class Problem:
                                    out.ctypes.data_as(C.c_void_p), int(nthreads))
         return out
 
+    def bsplineop_accumulate_complex(self, d, alpha: complex, x, beta: complex = 0.0, y=None):
+        """y <- alpha D^(d) x + beta y per row of x (nrhs, n): suzerain_bsplineop_accumulate_complex
+        (suzerain/bsplineop.c:260-297) through the reference's own zgbmv_d_z."""
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        nrhs, n = x.shape
+        out = (np.zeros_like(x) if y is None else np.array(y, dtype=np.complex128, order="C", copy=True))
+        a2 = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+        b2 = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+        lib().ref_bsplineop_accumulate_complex(int(d), int(nrhs), a2, x.ctypes.data_as(C.c_void_p), 1, n, b2,
+                                               out.ctypes.data_as(C.c_void_p), 1, n, C.byref(self.w))
+        return out
+
 
 def zgbsv_T(N, KL, KU, LU, B):
     """In-place zgbtrf + zgbtrs('T') on LAPACK band storage.
@@ -204,3 +216,25 @@ def zgbsv_T(N, KL, KU, LU, B):
 
 def q(S, n, i):
     return lib().suzerain_bsmbsm_q(S, n, i) if hasattr(lib(), "suzerain_bsmbsm_q") else (i % S) * n + i // S
+
+
+def diffwave(dxcnt, dzcnt, alpha: complex, x, Lx, Lz, grid, beta: complex | None = None, y=None):
+    """suzerain_diffwave_apply (beta is None: returns alpha D x) or suzerain_diffwave_accumulate
+    (returns alpha D x + beta y), suzerain/diffwave.c:65-198.  x, y: (nz, nx, Ny) complex128 with
+    grid = (Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez)."""
+    L = lib()
+    Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez = [int(v) for v in grid]
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    Ny = x.shape[-1]
+    a2 = (C.c_double * 2)(alpha.real, alpha.imag)
+    if beta is None:
+        out = x.copy()
+        L.ref_diffwave_apply(int(dxcnt), int(dzcnt), a2, out.ctypes.data_as(C.c_void_p), C.c_double(Lx),
+                             C.c_double(Lz), Ny, Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez)
+        return out
+    out = np.ascontiguousarray(y, dtype=np.complex128).copy()
+    b2 = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+    L.ref_diffwave_accumulate(int(dxcnt), int(dzcnt), a2, x.ctypes.data_as(C.c_void_p), b2,
+                              out.ctypes.data_as(C.c_void_p), C.c_double(Lx), C.c_double(Lz), Ny,
+                              Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez)
+    return out

@@ -285,3 +285,37 @@ int ref_zgbsv_T(int N, int KL, int KU, complex_double *LU, int ldlu,
     if (!info) info = suzerain_lapack_zgbtrs('T', N, KL, KU, nrhs, LU, ldlu, ipiv, B, N);
     return info;
 }
+
+/* suzerain_bsplineop_accumulate_complex (suzerain/bsplineop.c:260-297) restated around the
+ * reference's own suzerain_blas_zgbmv_d_z: bsplineop.c itself needs GSL (absent) for the
+ * operator construction it also contains. */
+void ref_bsplineop_accumulate_complex(int nderiv, int nrhs, const double alpha[2],
+        const complex_double *x, int incx, int ldx, const double beta[2],
+        complex_double *y, int incy, int ldy, const suzerain_bsplineop_workspace *w)
+{
+    const complex_double a = alpha[0] + _Complex_I * alpha[1], b = beta[0] + _Complex_I * beta[1];
+    for (int j = 0; j < nrhs; ++j)
+        suzerain_blas_zgbmv_d_z('T', w->n, w->n, w->kl[nderiv], w->ku[nderiv], a, w->D_T[nderiv], w->ld,
+                                x + (size_t) j * ldx, incx, b, y + (size_t) j * ldy, incy);
+}
+
+/* by-pointer wrappers: ctypes cannot pass C99 complex by value */
+void suzerain_diffwave_apply(int, int, complex_double, complex_double *, double, double, int,
+                             int, int, int, int, int, int, int, int);
+void suzerain_diffwave_accumulate(int, int, complex_double, const complex_double *, complex_double,
+                                  complex_double *, double, double, int, int, int, int, int, int, int, int, int);
+void ref_diffwave_apply(int dxcnt, int dzcnt, const double alpha[2], complex_double *x,
+        double Lx, double Lz, int Ny, int Nx, int dNx, int dkbx, int dkex,
+        int Nz, int dNz, int dkbz, int dkez)
+{
+    suzerain_diffwave_apply(dxcnt, dzcnt, alpha[0] + _Complex_I * alpha[1], x, Lx, Lz, Ny,
+                            Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez);
+}
+void ref_diffwave_accumulate(int dxcnt, int dzcnt, const double alpha[2], const complex_double *x,
+        const double beta[2], complex_double *y, double Lx, double Lz, int Ny,
+        int Nx, int dNx, int dkbx, int dkex, int Nz, int dNz, int dkbz, int dkez)
+{
+    suzerain_diffwave_accumulate(dxcnt, dzcnt, alpha[0] + _Complex_I * alpha[1], x,
+                                 beta[0] + _Complex_I * beta[1], y, Lx, Lz, Ny,
+                                 Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez);
+}

@@ -6,7 +6,9 @@ of the reference's operator interface used by tests and ``bench.py``.
 """
 from . import lib  # noqa: F401
 from .api import (BsplineOp, ImexOp, OperatorHybridIsothermal, OperatorHybridIsothermalDevice, SolverSpec,  # noqa: F401
+                  bsplineop_accumulate_complex_batch, diffwave_accumulate, diffwave_apply,
                   htstretch_breakpoints, wavegrid, wavenumbers)
 
 __all__ = ["lib", "BsplineOp", "ImexOp", "OperatorHybridIsothermal", "OperatorHybridIsothermalDevice", "SolverSpec",
+           "bsplineop_accumulate_complex_batch", "diffwave_accumulate", "diffwave_apply",
            "htstretch_breakpoints", "wavegrid", "wavenumbers"]

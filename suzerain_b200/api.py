@@ -288,6 +288,48 @@ def wavenumbers(g):
     return km, kn, act.astype(bool)
 
 
+def bsplineop_accumulate_complex_batch(bop, d, alpha, x, beta, y, stream=None):
+    """y <- alpha D^(d) x + beta y over the rows of the device tensors x, y (nrhs, n) complex128:
+    suzerain_bsplineop_accumulate_complex as batched by operator_tools.hpp:77-116."""
+    import torch
+    assert x.is_cuda and y.is_cuda and x.dtype == torch.complex128 and y.dtype == torch.complex128
+    nrhs = x.shape[0]
+    st = stream or torch.cuda.current_stream(x.device)
+    a2 = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    b2 = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+    rc = _L.load().szb_bsplineop_accumulate_complex_batch(
+        bop.handle, int(d), int(nrhs), a2, C.c_void_p(x.data_ptr()), x.stride(0), b2,
+        C.c_void_p(y.data_ptr()), y.stride(0), C.c_void_p(st.cuda_stream))
+    _L.check("szb_bsplineop_accumulate_complex_batch", rc)
+    return y
+
+
+def diffwave_apply(dxcnt, dzcnt, alpha, x, grid, stream=None):
+    """x <- alpha (i kx)^dxcnt (i kz)^dzcnt x in place on the device tensor x (nz, nx, Ny):
+    suzerain_diffwave_apply (suzerain/diffwave.c:65-129)."""
+    import torch
+    st = stream or torch.cuda.current_stream(x.device)
+    a2 = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    rc = _L.load().szb_diffwave_apply_batch(int(dxcnt), int(dzcnt), a2, C.c_void_p(x.data_ptr()),
+                                            C.byref(grid), int(x.shape[-1]), C.c_void_p(st.cuda_stream))
+    _L.check("szb_diffwave_apply_batch", rc)
+    return x
+
+
+def diffwave_accumulate(dxcnt, dzcnt, alpha, x, beta, y, grid, stream=None):
+    """y <- alpha (i kx)^dxcnt (i kz)^dzcnt x + beta y on device tensors (nz, nx, Ny):
+    suzerain_diffwave_accumulate (suzerain/diffwave.c:131-198)."""
+    import torch
+    st = stream or torch.cuda.current_stream(x.device)
+    a2 = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    b2 = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+    rc = _L.load().szb_diffwave_accumulate_batch(int(dxcnt), int(dzcnt), a2, C.c_void_p(x.data_ptr()), b2,
+                                                 C.c_void_p(y.data_ptr()), C.byref(grid), int(x.shape[-1]),
+                                                 C.c_void_p(st.cuda_stream))
+    _L.check("szb_diffwave_accumulate_batch", rc)
+    return y
+
+
 class OperatorHybridIsothermal:
     """The three virtuals of operator_hybrid_isothermal on HOST state arrays
     (numpy, optionally pinned); copies to the device and back inside each call

@@ -253,7 +253,7 @@ int szb_bsplineop_from_storage(int k, int n, int nderiv, const int *kl,
     return 0;
 }
 
-void szb_bsplineop_free(szb_bsplineop *w) { delete w; }
+void szb_bsplineop_free(szb_bsplineop *w) { if (w && w->d_Dr) cudaFree(w->d_Dr); delete w; }
 int szb_bsplineop_k     (const szb_bsplineop *w) { return w->k; }
 int szb_bsplineop_n     (const szb_bsplineop *w) { return w->n; }
 int szb_bsplineop_nderiv(const szb_bsplineop *w) { return w->nderiv; }

@@ -36,61 +36,9 @@ int make_temp_op(const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_re
     return szb_imexop_set_nrbc(t.op, a, b, c);
 }
 
-// y <- alpha D x + beta y, one thread per output point, grid-stride over rhs
-__global__ void bsplineop_accumulate_kernel(const double *Dt, int n, int kl, int ku, int ld,
-                                            int nrhs, cplx alpha, const cplx *x, size_t ldx,
-                                            cplx beta, cplx *y, size_t ldy)
-{
-    // Dt: the reference's D_T[d] view with max bandwidths: Dt[i*ld + (ku + j - i)] = D[i, j]
-    const size_t total = (size_t) nrhs * n;
-    for (size_t e = blockIdx.x * (size_t) blockDim.x + threadIdx.x; e < total;
-         e += (size_t) gridDim.x * blockDim.x) {
-        const size_t rhs = e / n; const int i = (int) (e - rhs * n);
-        const cplx *xv = x + rhs * ldx;
-        cplx s(0.0, 0.0);
-        const int j0 = max(0, i - ku), j1 = min(n - 1, i + kl);
-        for (int j = j0; j <= j1; ++j) addmul(s, xv[j], Dt[(size_t) i * ld + (ku + j - i)]);
-        cplx *yv = y + rhs * ldy + i;
-        *yv = is_zero(beta) ? alpha * s : alpha * s + beta * (*yv);
-    }
-}
-
 }  // namespace
 
 extern "C" {
-
-int szb_bsplineop_accumulate_complex_batch(const szb_bsplineop *w, int d, int nrhs,
-        const double alpha[2], const szb_complex *d_x, size_t ldx,
-        const double beta[2], szb_complex *d_y, size_t ldy, void *stream)
-{
-    if (!w) return -1;
-    if (d < 0 || d > w->nderiv) return -2;
-    if (nrhs < 0) return -3;
-    if (!alpha) return -4;
-    if (!d_x) return -5;
-    if (ldx < (size_t) w->n) return -6;
-    if (!beta) return -7;
-    if (!d_y) return -8;
-    if (ldy < (size_t) w->n) return -9;
-    if (nrhs == 0) return 0;
-    // operator rows are tiny; ship them with the call (setup-time path for the
-    // nonlinear operator's caller; the hot L path keeps its own device copy)
-    DevBuf<double> D;
-    const size_t cnt = (size_t) w->ld * w->n;
-    SZB_CUDA_OK(D.alloc(cnt));
-    SZB_CUDA_OK(cudaMemcpyAsync(D.p, w->storage.data() + (size_t) d * cnt, sizeof(double) * cnt,
-                                cudaMemcpyHostToDevice, (cudaStream_t) stream));
-    const size_t total = (size_t) nrhs * w->n;
-    const unsigned blocks = (unsigned) ((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-    bsplineop_accumulate_kernel<<<blocks, 256, 0, (cudaStream_t) stream>>>(
-        D.p, w->n, w->max_kl, w->max_ku, w->ld, nrhs, cplx(alpha[0], alpha[1]),
-        reinterpret_cast<const cplx *>(d_x), ldx, cplx(beta[0], beta[1]),
-        reinterpret_cast<cplx *>(d_y), ldy);
-    count_launch();
-    SZB_CUDA_OK(cudaGetLastError());
-    SZB_CUDA_OK(cudaStreamSynchronize((cudaStream_t) stream));
-    return 0;
-}
 
 int szb_rholut_imexop_accumulate(const double phi[2], double km, double kn,
         const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,

@@ -78,6 +78,8 @@ struct szb_bsplineop {
     std::vector<double> greville;      // n
     std::vector<double> storage;       // (nderiv+1) * ld * n, reference layout
     const double *D_T(int d) const { return storage.data() + (size_t) d * ld * n + (max_ku - ku[d]); }
+    mutable double *d_Dr = nullptr;    // device copy, r-major (auxops.cu), made on first batched apply
+    mutable int d_dev = -1;
 };
 
 struct szb_imexop {

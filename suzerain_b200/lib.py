@@ -86,6 +86,9 @@ PROTOTYPES = {
     "szb_bsplineop_accumulate_complex_batch": (C.c_int, [c_void_p, C.c_int, C.c_int, D2, c_void_p,
                                                          C.c_size_t, D2, c_void_p, C.c_size_t,
                                                          c_void_p]),
+    "szb_diffwave_apply_batch": (C.c_int, [C.c_int, C.c_int, D2, c_void_p, c_void_p, C.c_int, c_void_p]),
+    "szb_diffwave_accumulate_batch": (C.c_int, [C.c_int, C.c_int, D2, c_void_p, D2, c_void_p, c_void_p,
+                                                C.c_int, c_void_p]),
     "szb_zgbsv_spec_default": (ZgbsvSpec, []),
     "szb_imexop_create": (C.c_int, [c_void_p, C.POINTER(c_void_p)]),
     "szb_imexop_destroy": (None, [c_void_p]),
