@@ -4,8 +4,8 @@
 //  * szb_bsplineop_accumulate_complex_batch: y <- alpha D^(d) x + beta y over nrhs wall-normal
 //    pencils (suzerain_bsplineop_accumulate_complex, suzerain/bsplineop.c:260-297, as batched
 //    by operator_tools.hpp:77-116 over all local (kx,kz)).  Persistent CTAs; the pencils of the
-//    next group arrive by TMA bulk copies into a zero-halo double buffer while the current
-//    group is computed; the operator (ld x n doubles, r-major) stays in L1.
+//    next three groups are in flight as TMA bulk copies into a zero-halo ring while the current
+//    group is computed (about 100 KB per SM on the wire: the latency x bandwidth product of HBM); the operator (ld x n doubles, r-major) stays in L1.
 //  * szb_diffwave_{apply,accumulate}_batch: x <- alpha (i kx)^dx (i kz)^dz x  /
 //    y <- alpha (i kx)^dx (i kz)^dz x + beta y with dealiased and Nyquist modes zeroed
 //    (suzerain_diffwave_apply / _accumulate, suzerain/diffwave.c:65-198).  One warp per pencil:
@@ -23,6 +23,8 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // batched banded operator apply
 // ------------------------------------------------------------------------------------------
+constexpr int BOP_STAGES = 4;
+
 struct BopArgs {
     const double *Dr;       // [ld][n]  Dr[r*n + i] = D[i, i - ku + r]
     int n, kl, ku, ld, nrhs, group, nthr;
@@ -35,12 +37,13 @@ __global__ void __launch_bounds__(512)
 bop_accumulate_kernel(const BopArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long s_mbar[2];
+    constexpr int NST = BOP_STAGES;                                // ring depth: enough bytes in flight per SM
+    __shared__ __align__(8) unsigned long long s_mbar[NST];
     const int n = A.n, np = n + A.kl + A.ku, G = A.group;
-    cplx *s_x = reinterpret_cast<cplx *>(smem_raw);                // [2][G][ku + n + kl]
-    for (int e = threadIdx.x; e < 2 * G * np; e += blockDim.x) s_x[e] = cplx(0.0, 0.0);
+    cplx *s_x = reinterpret_cast<cplx *>(smem_raw);                // [NST][G][ku + n + kl]
+    for (int e = threadIdx.x; e < NST * G * np; e += blockDim.x) s_x[e] = cplx(0.0, 0.0);
     if (threadIdx.x == 0) {
-        fused::mbar_init(&s_mbar[0], 1); fused::mbar_init(&s_mbar[1], 1);
+        for (int b = 0; b < NST; ++b) fused::mbar_init(&s_mbar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -54,19 +57,22 @@ bop_accumulate_kernel(const BopArgs A)
             fused::tma_bulk_g2s(s_x + (stage * G + q) * np + A.ku, A.x + (size_t) (r0 + q) * A.ldx, bytes,
                                 &s_mbar[stage]);
     };
-    if (threadIdx.x == 0 && (int) blockIdx.x < ngroups) fetch(blockIdx.x, 0);
+    if (threadIdx.x == 0)
+        for (int b = 0; b < NST - 1; ++b)
+            if ((int) (blockIdx.x + b * gridDim.x) < ngroups) fetch(blockIdx.x + b * gridDim.x, b);
     const int q = threadIdx.x / A.nthr, i = threadIdx.x - q * A.nthr;
     const bool beta_zero = is_zero(A.beta);
     int it = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
-        const int stage = it & 1;
-        if (threadIdx.x == 0 && g + (int) gridDim.x < ngroups) fetch(g + gridDim.x, stage ^ 1);
+        const int stage = it % NST;
+        if (threadIdx.x == 0 && g + (NST - 1) * (int) gridDim.x < ngroups)
+            fetch(g + (NST - 1) * gridDim.x, (it + NST - 1) % NST);
         const int rhs = g * G + q;
         cplx yold(0.0, 0.0);
         const bool live = i < n && rhs < A.nrhs;
         cplx *yp = A.y + (size_t) rhs * A.ldy + i;
         if (live && !beta_zero) yold = *yp;                       // in flight while the tile lands
-        fused::mbar_wait(&s_mbar[stage], (it >> 1) & 1);
+        fused::mbar_wait(&s_mbar[stage], (it / NST) & 1);
         if (live) {
             const cplx *xs = s_x + (stage * G + q) * np + i;       // xs[r] = x[i - ku + r]
             const double *D = A.Dr + i;
@@ -207,7 +213,7 @@ int szb_bsplineop_accumulate_complex_batch(const szb_bsplineop *w, int d, int nr
     A.alpha = cplx(alpha[0], alpha[1]); A.beta = cplx(beta[0], beta[1]);
     A.x = reinterpret_cast<const cplx *>(d_x); A.ldx = ldx;
     A.y = reinterpret_cast<cplx *>(d_y); A.ldy = ldy;
-    const size_t smem = sizeof(cplx) * 2 * (size_t) A.group * (A.n + A.kl + A.ku);
+    const size_t smem = sizeof(cplx) * BOP_STAGES * (size_t) A.group * (A.n + A.kl + A.ku);
     if (smem > 48 * 1024)
         SZB_CUDA_OK(cudaFuncSetAttribute(bop_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     int sms = 148;
