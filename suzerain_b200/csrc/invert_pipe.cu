@@ -32,6 +32,7 @@
 // Arithmetic per element is the same sequence of FMAs as the unblocked zgbtf2 sweep;
 // the pivot rule is izamax's (first maximum of |re|+|im|), so ipiv is LAPACK's.
 #include <climits>
+#include <cstdlib>
 #include <cstdio>
 
 #include "invert_common.cuh"
@@ -96,6 +97,7 @@ struct PipeArgs {
     cplx *state; size_t fs, ps;
     int *ipiv_out, *info_out, *iters_out;
     cplx *lwork;            // per CTA: 2 buffers of N*KL multipliers
+    cplx *vwork;            // per CTA: 2 buffers of N (b -> y -> x) when they do not fit in shared memory
     int zero_wall_rhs;      // zero the wall rows of the right hand side (not for refinement residuals)
 };
 
@@ -142,15 +144,16 @@ struct PipeLayout {
     static constexpr size_t tref = misc + 4 * 32;
     static constexpr size_t tblk = tref + MAXTERMS;
     static constexpr size_t v = (tblk + 80 + 15) / 16 * 16;
-    __host__ __device__ static constexpr size_t ipiv(int N) { return v + C * 2 * (size_t) N; }
-    __host__ __device__ static constexpr size_t bytes(int N) { return (ipiv(N) + 2 * (size_t) N + 15) / 16 * 16; }
+    // vg: the b -> y -> x vectors live in global memory (large N), only ipiv follows
+    __host__ __device__ static constexpr size_t ipiv(int N, bool vg = false) { return vg ? v : v + C * 2 * (size_t) N; }
+    __host__ __device__ static constexpr size_t bytes(int N, bool vg = false) { return (ipiv(N, vg) + 2 * (size_t) N + 15) / 16 * 16; }
 };
 
 template <class W>
-__host__ __device__ inline size_t pipe_smem_bytes(int N) { return PipeLayout<W>::bytes(N); }
+__host__ __device__ inline size_t pipe_smem_bytes(int N, bool vg = false) { return PipeLayout<W>::bytes(N, vg); }
 
 template <class W>
-__device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
+__device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N, bool vg)
 {
     using Y = PipeLayout<W>;
     PSmem<W> S;
@@ -170,7 +173,7 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N)
     S.tref = raw + Y::tref;
     S.tblk = raw + Y::tblk;
     S.v = reinterpret_cast<cplx *>(raw + Y::v);
-    S.ipiv = raw + Y::ipiv(N);
+    S.ipiv = raw + Y::ipiv(N, vg);
     return S;
 }
 
@@ -223,6 +226,14 @@ __device__ __forceinline__ int2 lds_i2(unsigned sa)
     int2 v;
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sa) : "memory");
     return v;
+}
+// b / y / x vectors: shared memory, or (VG) global memory read at L2 so that values written by
+// other warps of the CTA are seen
+template <bool VG>
+__device__ __forceinline__ cplx ldv(const cplx *p)
+{
+    if (VG) { const double2 t = __ldcg(reinterpret_cast<const double2 *>(p)); return cplx(t.x, t.y); }
+    return *p;
 }
 // keep a value in a register instead of letting the compiler recompute it (S2R / LDC chains)
 // inside the panel warp's column loop
@@ -341,14 +352,15 @@ __device__ __forceinline__ void lookahead_phases(const SM &S, unsigned sbase, in
     bar_sync_n<1>(NT);
 }
 
-template <class W>
+template <class W, bool VG>
 __global__ void __maxnreg__(W::MAXR)
 invert_pipe_kernel(const PipeArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const PackArgs &K = A.pk;
     const int N = K.N, n = K.n;
-    const PSmem<W> S = pipe_carve<W>(smem_raw, N);
+    const PSmem<W> S = pipe_carve<W>(smem_raw, N, VG);
+    cplx *const vbase = VG ? A.vwork + (size_t) blockIdx.x * 2 * N : S.v;
     // logical thread index: warps are dealt to the four SM sub-partitions round-robin, so the
     // roles are permuted to keep the latency-critical panel warps away from the FP64-heavy
     // update warps (see PipeCfg::logical_warp)
@@ -378,7 +390,7 @@ invert_pipe_kernel(const PipeArgs A)
         for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
             const int buf = q & 1;
             if (buf == 0) bar_sync_n<BAR_FULL0>(W::NTH); else bar_sync_n<BAR_FULL1>(W::NTH);
-            cplx *x = S.v + (size_t) buf * N;
+            cplx *x = vbase + (size_t) buf * N;
             const unsigned char *jpv = S.ipiv + (size_t) buf * N;
             const cplx *Lg = lwork + (size_t) buf * lstride;
             const int info = S.misc[buf];
@@ -417,7 +429,7 @@ invert_pipe_kernel(const PipeArgs A)
                         for (int t = lane; t < KL; t += 32) {
                             const int pz = jhi + 1 + t;
                             if (pz <= N - 1) {
-                                const cplx xv = x[pz];
+                                const cplx xv = ldv<VG>(x + pz);
 #pragma unroll
                                 for (int qq = 0; qq < 4; ++qq) {
                                     const int i = pz - (jlo + qq);                 // >= 1
@@ -460,10 +472,10 @@ invert_pipe_kernel(const PipeArgs A)
                             const cplx s0(S.sred[0], S.sred[1]), s1(S.sred[2], S.sred[3]);
                             const cplx s2(S.sred[4], S.sred[5]), s3(S.sred[6], S.sred[7]);
                             const cplx *L0 = Lc, *L1 = Lc + KL, *L2 = Lc + 2 * KL;
-                            const cplx x3 = x[jlo + 3] - s3;
-                            cplx x2 = x[jlo + 2] - s2; submul(x2, L2[0], x3);
-                            cplx x1 = x[jlo + 1] - s1; submul(x1, L1[0], x2); submul(x1, L1[1], x3);
-                            cplx x0 = x[jlo] - s0; submul(x0, L0[0], x1); submul(x0, L0[1], x2); submul(x0, L0[2], x3);
+                            const cplx x3 = ldv<VG>(x + jlo + 3) - s3;
+                            cplx x2 = ldv<VG>(x + jlo + 2) - s2; submul(x2, L2[0], x3);
+                            cplx x1 = ldv<VG>(x + jlo + 1) - s1; submul(x1, L1[0], x2); submul(x1, L1[1], x3);
+                            cplx x0 = ldv<VG>(x + jlo) - s0; submul(x0, L0[0], x1); submul(x0, L0[1], x2); submul(x0, L0[2], x3);
                             x[jlo + 3] = x3; x[jlo + 2] = x2; x[jlo + 1] = x1; x[jlo] = x0;
                         }
                         __syncwarp();
@@ -472,16 +484,16 @@ invert_pipe_kernel(const PipeArgs A)
                         const int lm = min(KL, N - 1 - j);
                         const cplx *Lj = Lc + (size_t) (j - jlo) * KL;
                         cplx s(0.0, 0.0);
-                        for (int i = 1 + lane; i <= lm; i += 32) addmul(s, Lj[i - 1], x[j + i]);
+                        for (int i = 1 + lane; i <= lm; i += 32) addmul(s, Lj[i - 1], ldv<VG>(x + j + i));
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) {
                             s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
                             s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
                         }
                         if (lane == 0) {
-                            cplx v = x[j] - s;
+                            cplx v = ldv<VG>(x + j) - s;
                             const int l = j + jpv[j];
-                            if (l != j) { const cplx t = x[l]; x[l] = v; v = t; }
+                            if (l != j) { const cplx t = ldv<VG>(x + l); x[l] = v; v = t; }
                             x[j] = v;
                         }
                         __syncwarp();
@@ -504,7 +516,7 @@ invert_pipe_kernel(const PipeArgs A)
                 cplx *v = A.state + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
                 for (int e = lane; e < N; e += 32) {
                     const int f = e / n, y = e - f * n;
-                    v[(size_t) f * A.fs + y] = x[5 * y + f];
+                    v[(size_t) f * A.fs + y] = ldv<VG>(x + 5 * y + f);
                 }
             }
             if (lane == 0) {
@@ -529,7 +541,7 @@ invert_pipe_kernel(const PipeArgs A)
     for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
         const int buf = q & 1;
         if (q >= 2) { if (buf == 0) bar_sync_n<BAR_EMPTY0>(W::NTH); else bar_sync_n<BAR_EMPTY1>(W::NTH); }
-        cplx *sv = S.v + (size_t) buf * N;
+        cplx *sv = vbase + (size_t) buf * N;
         unsigned char *jpv = S.ipiv + (size_t) buf * N;
         cplx *Lg = lwork + (size_t) buf * lstride;
         const double km = K.km[p], kn = K.kn[p];
@@ -556,7 +568,7 @@ invert_pipe_kernel(const PipeArgs A)
         // initial window: logical rows 0..RW-1 in slots 0..RW-1; RHS row t_c = b_c
         for (int blk = 0; blk < RW / 5; ++blk)
             assemble_block<W>(K, S, km, kn, blk, S.win + (size_t) blk * P * CW, tid, NT);
-        for (int c = tid; c < CW; c += NT) S.win[(size_t) RW * CW + c] = c < N ? sv[c] : cplx(0.0, 0.0);
+        for (int c = tid; c < CW; c += NT) S.win[(size_t) RW * CW + c] = c < N ? ldv<VG>(sv + c) : cplx(0.0, 0.0);
         // operator rows / profile column for the first block assembled inside the panel loop
         stage_rowblock<W>(K, S, RW / 5, 0, tid, NT);
         bar_sync_n<BAR_ALL>(NT);
@@ -576,7 +588,7 @@ invert_pipe_kernel(const PipeArgs A)
             int pk = slot < NS ? P : -1;
             cplx a[P];
             unsigned rec_sa = sbase + (unsigned) Y::rec, sv_sa = sbase + (unsigned) (Y::v + sizeof(cplx) * (size_t) buf * N);
-            unsigned jpv_sa = sbase + (unsigned) (Y::ipiv(N) + (size_t) buf * N), xmh_sa = sbase + (unsigned) Y::misc + 48;
+            unsigned jpv_sa = sbase + (unsigned) (Y::ipiv(N, VG) + (size_t) buf * N), xmh_sa = sbase + (unsigned) Y::misc + 48;
             pin(rec_sa); pin(sv_sa); pin(jpv_sa); pin(xmh_sa);
             // (b) lane predicates as pinned registers (the compiler otherwise re-reads SR_TID)
             int is_lead = tid == NTU + W::NTA, is_rhs = slot == RW, is_l0 = lane == 0;
@@ -710,7 +722,7 @@ invert_pipe_kernel(const PipeArgs A)
                         // diagonal), in zgbtf2 order to the scratch, y = b^T U^-1 from the RHS row
                         sts_if(lp_sa + 16 * k, l, pk >= 0);
                         st_global_if(Lcol + lg, l, act && lg <= hi);
-                        sts_if(sv_sa + 16 * col, l, is_rhs);
+                        if (VG) st_global_if(sv + col, l, is_rhs); else sts_if(sv_sa + 16 * col, l, is_rhs);
 #pragma unroll
                         for (int m = 1; m < P; ++m) {
                             cplx t = a[m];
@@ -814,7 +826,7 @@ invert_pipe_kernel(const PipeArgs A)
                         int ccs = jco + m; if (ccs >= CW) ccs -= CW;
                         const int cn = jo + CW + m;
                         if (e < NS * P) {
-                            if (s == RW) S.win[(size_t) RW * CW + ccs] = cn < N ? sv[cn] : cplx(0.0, 0.0);
+                            if (s == RW) S.win[(size_t) RW * CW + ccs] = cn < N ? ldv<VG>(sv + cn) : cplx(0.0, 0.0);
                             else if (!((omask >> s) & 1)) S.win[(size_t) s * CW + ccs] = cplx(0.0, 0.0);
                         }
                     }
@@ -862,25 +874,27 @@ invert_pipe_kernel(const PipeArgs A)
     }
 }
 
-template <class W>
-int launch_pipe(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
+template <class W, bool VG>
+int launch_pipe_vg(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
 {
     const int N = op->A.N;
-    const size_t smem = pipe_smem_bytes<W>(N);
+    const size_t smem = pipe_smem_bytes<W>(N, VG);
     if (smem > 227 * 1024) return 1;                 // caller falls back to another kernel
     static bool configured = false;
     if (!configured) {
-        SZB_CUDA_OK(cudaFuncSetAttribute(invert_pipe_kernel<W>,
+        SZB_CUDA_OK(cudaFuncSetAttribute(invert_pipe_kernel<W, VG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     int per_sm = 0;
-    SZB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, invert_pipe_kernel<W>,
+    SZB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, invert_pipe_kernel<W, VG>,
                                                               W::NTH, smem));
     if (per_sm < 1) return 1;
     int slots = op->sm_count * per_sm;
     if (slots > npencil) slots = npencil;
-    const size_t need = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
+    const size_t lbytes = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
+    const size_t vbytes = VG ? (size_t) slots * 2 * N * sizeof(cplx) : 0;
+    const size_t need = lbytes + vbytes;
     if (need > op->work_bytes) {
         if (op->d_work) SZB_CUDA_OK(cudaFree(op->d_work));
         op->d_work = nullptr; op->work_bytes = 0;
@@ -889,10 +903,24 @@ int launch_pipe(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t str
     }
     op->work_slots = slots;
     A.lwork = static_cast<cplx *>(op->d_work);
-    invert_pipe_kernel<W><<<slots, W::NTH, smem, stream>>>(A);
+    A.vwork = VG ? reinterpret_cast<cplx *>(static_cast<unsigned char *>(op->d_work) + lbytes) : nullptr;
+    invert_pipe_kernel<W, VG><<<slots, W::NTH, smem, stream>>>(A);
     count_launch();
     SZB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// The b -> y -> x vectors (2 N complex per CTA) stay in shared memory while two CTAs still fit
+// an SM with them; beyond that (Ny >= 256 at k = 8) they move to a global scratch read at L2.
+template <class W>
+int launch_pipe(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
+{
+    const size_t two_per_sm = (233472 - 2 * 1024) / 2;
+    static const bool allow = [] { const char *e = std::getenv("SZB_PIPE_VG"); return !(e && e[0] == '0'); }();
+    if (allow && W::MINB >= 2 && pipe_smem_bytes<W>(op->A.N, false) > two_per_sm
+        && pipe_smem_bytes<W>(op->A.N, true) <= two_per_sm)
+        return launch_pipe_vg<W, true>(op, A, npencil, stream);
+    return launch_pipe_vg<W, false>(op, A, npencil, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -1077,7 +1105,7 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     A.npencil = npencil; A.index = d_index;
     A.state = d_state; A.fs = fs; A.ps = ps;
     A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
-    A.lwork = nullptr;
+    A.lwork = nullptr; A.vwork = nullptr;
     A.zero_wall_rhs = zero_wall_rhs;
     if (op->A.KL != op->A.KU) return 1;
     switch (op->A.KL) {
