@@ -208,7 +208,7 @@ int build_ctx(const szb_wavegrid *g, FieldCtx &F)
     // chunks keep upload, compute and download overlapped.  For invert every chunk is one
     // launch of the persistent kernel and pays its tail (slots idling until the slowest pencil
     // of the chunk is done) while only the first upload and the last download are exposed: a
-    // short first and last chunk (1/16 of the rows each) and two long ones in between.
+    // short first and last chunk (1/8 of the rows each) around one long one.
     int nrows_active = 0;
     for (int r = 0; r < F.nz; ++r) nrows_active += row_active[r];
     auto cut = [&](std::vector<int> sizes, std::vector<Chunk> &out) {
@@ -230,8 +230,8 @@ int build_ctx(const szb_wavegrid *g, FieldCtx &F)
     };
     cut(std::vector<int>(8, nrows_active ? (nrows_active + 7) / 8 : 1), F.chunks);
     if (nrows_active >= 32) {
-        const int edge = nrows_active / 16, mid = nrows_active - 2 * edge;
-        cut({ edge, (mid + 1) / 2, mid / 2, edge }, F.chunks_inv);
+        const int edge = nrows_active / 8, mid = nrows_active - 2 * edge;
+        cut({ edge, mid, edge }, F.chunks_inv);
     } else {
         F.chunks_inv = F.chunks;
     }

@@ -319,6 +319,9 @@ __device__ __noinline__ double2 exact_recip(double x, double y)
 template <class W, class SM>
 __device__ __forceinline__ void lookahead_phases(const SM &S, unsigned sbase, int j, int jc, int par, int tid)
 {
+#ifdef SZB_PIPE_NOLOOK
+    return;
+#endif
     constexpr int NS = W::NS, CW = W::CW, NT = W::NT;
     const int *opiv = S.pivslot + (par ^ 1) * P;
     const cplx *lpo = S.lp + (size_t) (par ^ 1) * NS * P;
