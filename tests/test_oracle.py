@@ -305,3 +305,39 @@ def test_cabi_argument_checks_follow_lapack_convention():
                                      None, None) == -1
     out = C.c_void_p()
     assert L.szb_bsplineop_alloc(0, 4, None, 2, C.byref(out)) < 0
+
+
+def test_reference_diffwave_matches_formula():
+    """oracle/_ref now also carries the reference's suzerain/diffwave.c (built unmodified): check the
+    binding and the stub gsl_sf_pow_int against the closed form alpha (i kx)^dx (i kz)^dz x with
+    dealiased / Nyquist modes zeroed (suzerain/diffwave.c:65-198, inorder.h:282-293)."""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    Nx, dNx, Nz, dNz, Ny = 8, 12, 6, 9, 5
+    Lx, Lz = 4 * np.pi, 2.0
+    grid = (Nx, dNx, 0, dNx // 2 + 1, Nz, dNz, 0, dNz)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((dNz, dNx // 2 + 1, Ny)) + 1j * rng.standard_normal((dNz, dNx // 2 + 1, Ny))
+    y = rng.standard_normal(x.shape) + 1j * rng.standard_normal(x.shape)
+    alpha, beta = 0.7 - 0.3j, 1.5 + 0.25j
+
+    def freq(N, dN, i):                          # suzerain_inorder_wavenumber_diff
+        return i if i < (N + 1) // 2 else (-dN + i if i >= dN - (N - 1) // 2 else 0)
+
+    def absw(dN, i):
+        return i if i < dN // 2 + 1 else dN - i
+
+    for dx, dz in [(0, 0), (1, 0), (0, 2), (2, 1)]:
+        want = np.zeros_like(x)
+        for n in range(dNz):
+            keepn = freq(Nz, dNz, n) != 0 if dz > 0 else absw(dNz, n) <= (Nz - 1) // 2
+            for m in range(dNx // 2 + 1):
+                keepm = freq(Nx, dNx, m) != 0 if dx > 0 else absw(dNx, m) <= (Nx - 1) // 2
+                if keepn and keepm:
+                    kx, kz = 2 * np.pi / Lx * freq(Nx, dNx, m), 2 * np.pi / Lz * freq(Nz, dNz, n)
+                    want[n, m] = alpha * (1j * kx) ** dx * (1j * kz) ** dz * x[n, m]
+        got = oref.diffwave(dx, dz, alpha, x, Lx, Lz, grid)
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+        got = oref.diffwave(dx, dz, alpha, x, Lx, Lz, grid, beta=beta, y=y)
+        assert np.abs(got - (want + beta * y)).max() <= 1e-13 * np.abs(want + beta * y).max()
