@@ -169,6 +169,13 @@ int  szb_imexop_set_isothermal(szb_imexop *op, const szb_isothermal *iso);
 int  szb_imexop_set_nrbc(szb_imexop *op, const double *a, const double *b,
                          const double *c);
 szb_bsmbsm szb_imexop_bsmbsm(const szb_imexop *op);
+/* Which linearisation the implicit operator uses (apps/perfect/linearize_type.hpp, read at
+ * operator_hybrid_isothermal.cpp:136-241, 276-374, 608-761): rhome_xyz (default) or rhome_y, the
+ * wavenumber-independent operator of suzerain_rholut_imexop_{accumulate,packc,packf}00
+ * (suzerain/rholut_imexop.h:209-238, 330-368, 447-469): accumulate / apply then use km = kn = 0
+ * for every pencil and invert factors ONE operator and solves every pencil with it. */
+enum { SZB_LINEARIZE_RHOME_XYZ = 0, SZB_LINEARIZE_RHOME_Y = 1 };
+int  szb_imexop_set_linearization(szb_imexop *op, int linearization);
 
 /* Batched, device pointers.  Batch entry p works on the pencil whose field f
  * starts at
@@ -276,6 +283,25 @@ int szb_rholut_imexop_packf(const double phi[2], double km, double kn,
         const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
         szb_bsmbsm *A_T, szb_complex *patpt,
         const double *a, const double *b, const double *c);
+
+/* suzerain_rholut_imexop_{accumulate,packc,packf}00 (rholut_imexop.h:209-238, 330-368,
+ * 447-469): the km = kn = 0 special cases used by linearize::rhome_y. */
+int szb_rholut_imexop_accumulate00(const double phi[2],
+        const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,
+        const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
+        const szb_complex *in_rho_E, const szb_complex *in_rho_u,
+        const szb_complex *in_rho_v, const szb_complex *in_rho_w,
+        const szb_complex *in_rho, const double beta[2],
+        szb_complex *out_rho_E, szb_complex *out_rho_u, szb_complex *out_rho_v,
+        szb_complex *out_rho_w, szb_complex *out_rho, const double *c);
+int szb_rholut_imexop_packc00(const double phi[2],
+        const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,
+        const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
+        szb_bsmbsm *A_T, szb_complex *patpt, const double *c);
+int szb_rholut_imexop_packf00(const double phi[2],
+        const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,
+        const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
+        szb_bsmbsm *A_T, szb_complex *patpt, const double *c);
 
 /* ------------------------------------------------------------------------ *
  * Whole-field HOST-pointer entry points: the three virtuals of

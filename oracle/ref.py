@@ -189,6 +189,47 @@ class Problem:
                                    out.ctypes.data_as(C.c_void_p), int(nthreads))
         return out
 
+    # ---- linearize::rhome_y: the wavenumber-independent "00" operator ----
+    def assemble00(self, phi: complex, packf=False, with_bc=True):
+        rows = self.LD + (self.KL if packf else 0)
+        out = np.full((self.N, rows), np.nan + 1j * np.nan, dtype=np.complex128)
+        phi2 = (C.c_double * 2)(complex(phi).real, complex(phi).imag)
+        _, _, c = self._abc()
+        rc = lib().ref_assemble00(phi2, C.byref(self.scen), C.byref(self.ref), C.byref(self.refld),
+                                  C.byref(self.w),
+                                  C.byref(self.bc) if (with_bc and self.bc is not None) else None, c,
+                                  int(packf), out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return out
+
+    def invert00(self, phi: complex, state, want_ipiv=False):
+        """operator_hybrid_isothermal.cpp:691-761: one factorisation of the 00 operator, one
+        zgbtrs('T') per pencil."""
+        x = np.array(state, dtype=np.complex128, order="C", copy=True)
+        npencil = x.shape[0]
+        N = x.shape[1]
+        phi2 = (C.c_double * 2)(complex(phi).real, complex(phi).imag)
+        ipiv = np.zeros(N, dtype=np.int32)
+        _, _, c = self._abc()
+        info = lib().ref_invert00_batch(phi2, C.byref(self.scen), C.byref(self.ref), C.byref(self.refld),
+                                        C.byref(self.w), C.byref(self.bc), c, npencil,
+                                        x.ctypes.data_as(C.c_void_p), _p(ipiv, C.c_int))
+        res = dict(x=x, info=int(info))
+        if want_ipiv:
+            res["ipiv"] = ipiv
+        return res
+
+    def accumulate00(self, phi: complex, x, beta: complex = 0.0, y=None):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        out = (np.zeros_like(x) if y is None else np.array(y, dtype=np.complex128, order="C", copy=True))
+        phi2 = (C.c_double * 2)(complex(phi).real, complex(phi).imag)
+        beta2 = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+        _, _, c = self._abc()
+        lib().ref_accumulate00_batch(phi2, C.byref(self.scen), C.byref(self.ref), C.byref(self.refld),
+                                     C.byref(self.w), c, x.shape[0], x.ctypes.data_as(C.c_void_p), beta2,
+                                     out.ctypes.data_as(C.c_void_p))
+        return out
+
     def bsplineop_accumulate_complex(self, d, alpha: complex, x, beta: complex = 0.0, y=None):
         """y <- alpha D^(d) x + beta y per row of x (nrhs, n): suzerain_bsplineop_accumulate_complex
         (suzerain/bsplineop.c:260-297) through the reference's own zgbmv_d_z."""

@@ -319,3 +319,83 @@ void ref_diffwave_accumulate(int dxcnt, int dzcnt, const double alpha[2], const 
                                  beta[0] + _Complex_I * beta[1], y, Lx, Lz, Ny,
                                  Nx, dNx, dkbx, dkex, Nz, dNz, dkbz, dkez);
 }
+
+/* ---- linearize::rhome_y (apps/perfect/operator_hybrid_isothermal.cpp:691-761): ONE wavenumber-
+ * independent operator from suzerain_rholut_imexop_packf00, enforcer, one zgbtrf; then supply_B /
+ * rhs BC / zgbtrs('T') / demand_X per pencil.  state: npencil contiguous pencils of 5*n complex,
+ * solved in place; ipiv_out (may be NULL): N pivots.  Returns zgbtrf's info. ---- */
+int ref_invert00_batch(const double phi[2],
+                       const suzerain_rholut_imexop_scenario *s,
+                       const suzerain_rholut_imexop_ref *r,
+                       const suzerain_rholut_imexop_refld *ld,
+                       const suzerain_bsplineop_workspace *w,
+                       const ref_bc *bc, const double *c,
+                       int npencil, complex_double *state, int *ipiv_out)
+{
+    suzerain_bsmbsm A = suzerain_bsmbsm_construct(5, w->n, w->max_kl, w->max_ku);
+    const complex_double cphi = phi[0] + _Complex_I*phi[1];
+    const int N = A.N, ldlu = A.KL + A.LD;
+    const int nbuf = A.ld*A.n > 75 ? A.ld*A.n : 75;
+    complex_double *buf = (complex_double *) malloc(nbuf*sizeof(*buf));
+    complex_double *LU  = (complex_double *) malloc((size_t) ldlu*N*sizeof(*LU));
+    complex_double *PB  = (complex_double *) malloc(N*sizeof(*PB));
+    int *ipiv = (int *) malloc(N*sizeof(int));
+    suzerain_rholut_imexop_packf00(cphi, s, r, ld, w, 0, 1, 2, 3, 4, buf, &A, LU, c);
+    enforcer_op(&A, bc, LU + A.KL, ldlu);
+    int info = suzerain_lapack_zgbtrf(N, N, A.KL, A.KU, LU, ldlu, ipiv);
+    for (int p = 0; p < npencil && !info; ++p) {
+        complex_double * const x = state + (size_t) p*N;
+        suzerain_bsmbsm_zaPxpby('N', A.S, A.n, 1, x, 1, 0, PB, 1);
+        enforcer_rhs(&A, bc, PB);
+        info = suzerain_lapack_zgbtrs('T', N, A.KL, A.KU, 1, LU, ldlu, ipiv, PB, N);
+        if (!info) suzerain_bsmbsm_zaPxpby('T', A.S, A.n, 1, PB, 1, 0, x, 1);
+    }
+    if (ipiv_out) memcpy(ipiv_out, ipiv, N*sizeof(int));
+    free(buf); free(LU); free(PB); free(ipiv);
+    return info;
+}
+
+/* suzerain_rholut_imexop_accumulate00 over a batch (operator_hybrid_isothermal.cpp rhome_y branch
+ * of apply / accumulate) */
+void ref_accumulate00_batch(const double phi[2],
+                            const suzerain_rholut_imexop_scenario *s,
+                            const suzerain_rholut_imexop_ref *r,
+                            const suzerain_rholut_imexop_refld *ld,
+                            const suzerain_bsplineop_workspace *w, const double *c,
+                            int npencil, const complex_double *in, const double beta[2],
+                            complex_double *out)
+{
+    const complex_double cphi  = phi[0]  + _Complex_I*phi[1];
+    const complex_double cbeta = beta[0] + _Complex_I*beta[1];
+    const int n = w->n;
+    for (int p = 0; p < npencil; ++p) {
+        const complex_double *i0 = in  + (size_t) p*5*n;
+        complex_double       *o0 = out + (size_t) p*5*n;
+        suzerain_rholut_imexop_accumulate00(cphi, s, r, ld, w, i0, i0 + n, i0 + 2*n, i0 + 3*n, i0 + 4*n,
+                                            cbeta, o0, o0 + n, o0 + 2*n, o0 + 3*n, o0 + 4*n, c);
+    }
+}
+
+/* suzerain_rholut_imexop_pack{c,f}00 into out (as ref_assemble) */
+int ref_assemble00(const double phi[2],
+                   const suzerain_rholut_imexop_scenario *s,
+                   const suzerain_rholut_imexop_ref *r,
+                   const suzerain_rholut_imexop_refld *ld,
+                   const suzerain_bsplineop_workspace *w,
+                   const ref_bc *bc, const double *c, int packf, complex_double *out)
+{
+    suzerain_bsmbsm A = suzerain_bsmbsm_construct(5, w->n, w->max_kl, w->max_ku);
+    const int nbuf = A.ld*A.n > 75 ? A.ld*A.n : 75;
+    complex_double *buf = (complex_double *) malloc(nbuf*sizeof(*buf));
+    if (!buf) return -1;
+    const complex_double cphi = phi[0] + _Complex_I*phi[1];
+    if (packf) {
+        suzerain_rholut_imexop_packf00(cphi, s, r, ld, w, 0, 1, 2, 3, 4, buf, &A, out, c);
+        if (bc) enforcer_op(&A, bc, out + A.KL, A.LD + A.KL);
+    } else {
+        suzerain_rholut_imexop_packc00(cphi, s, r, ld, w, 0, 1, 2, 3, 4, buf, &A, out, c);
+        if (bc) enforcer_op(&A, bc, out, A.LD);
+    }
+    free(buf);
+    return 0;
+}

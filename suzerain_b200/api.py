@@ -229,6 +229,13 @@ class ImexOp:
         _L.check("szb_imexop_set_nrbc", _L.load().szb_imexop_set_nrbc(self.handle, *ptrs))
         return self
 
+    def set_linearization(self, mode="rhome_xyz"):
+        """linearize::rhome_xyz (default) or linearize::rhome_y, the wavenumber-independent operator
+        (apps/perfect/operator_hybrid_isothermal.cpp:691-761)."""
+        code = {"rhome_xyz": 0, "rhome_y": 1}[mode]
+        _L.check("szb_imexop_set_linearization", _L.load().szb_imexop_set_linearization(self.handle, code))
+        return self
+
     # ---- batched, device tensors ------------------------------------------------
     def accumulate_batch(self, phi, km, kn, x, beta, y, index=None, x_strides=None,
                          y_strides=None, stream=None):

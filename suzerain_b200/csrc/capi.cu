@@ -444,4 +444,36 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
     return 0;
 }
 
+/* The km = kn = 0 special cases (suzerain/rholut_imexop.h:209-238, 330-368, 447-469: "equivalent
+ * to calling ... using km == 0 and kn == 0"), used by linearize::rhome_y. */
+int szb_rholut_imexop_accumulate00(const double phi[2],
+        const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,
+        const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
+        const szb_complex *in_rho_E, const szb_complex *in_rho_u,
+        const szb_complex *in_rho_v, const szb_complex *in_rho_w,
+        const szb_complex *in_rho, const double beta[2],
+        szb_complex *out_rho_E, szb_complex *out_rho_u, szb_complex *out_rho_v,
+        szb_complex *out_rho_w, szb_complex *out_rho, const double *c)
+{
+    return szb_rholut_imexop_accumulate(phi, 0.0, 0.0, s, r, ld, w, in_rho_E, in_rho_u, in_rho_v, in_rho_w,
+                                        in_rho, beta, out_rho_E, out_rho_u, out_rho_v, out_rho_w, out_rho,
+                                        nullptr, nullptr, c);
+}
+
+int szb_rholut_imexop_packc00(const double phi[2],
+        const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,
+        const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
+        szb_bsmbsm *A_T, szb_complex *patpt, const double *c)
+{
+    return szb_rholut_imexop_packc(phi, 0.0, 0.0, s, r, ld, w, A_T, patpt, nullptr, nullptr, c);
+}
+
+int szb_rholut_imexop_packf00(const double phi[2],
+        const szb_rholut_imexop_scenario *s, const szb_rholut_imexop_ref *r,
+        const szb_rholut_imexop_refld *ld, const szb_bsplineop *w,
+        szb_bsmbsm *A_T, szb_complex *patpt, const double *c)
+{
+    return szb_rholut_imexop_packf(phi, 0.0, 0.0, s, r, ld, w, A_T, patpt, nullptr, nullptr, c);
+}
+
 }  // extern "C"

@@ -460,6 +460,26 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     if (!d_info) return -14;
     if (npencil == 0) return 0;
 
+    // linearize::rhome_y (operator_hybrid_isothermal.cpp:691-761): the operator does not depend on
+    // the wavenumbers.  zgbsv without extra right hand sides: one factorisation, one pair of
+    // triangular sweeps per pencil (rhome_y.cu); otherwise the general kernels at km = kn = 0.
+    if (op->linearization == SZB_LINEARIZE_RHOME_Y) {
+        if (spec->method == SZB_SOLVER_ZGBSV && nextra == 0) {
+            int rc = invert00_dispatch(op, phi, npencil, d_index, reinterpret_cast<cplx *>(d_state), field_stride,
+                                       pencil_stride, d_ipiv, d_info, (cudaStream_t) stream);
+            if (rc == 0 && d_iters) SZB_CUDA_OK(cudaMemsetAsync(d_iters, 0, sizeof(int) * (size_t) npencil, (cudaStream_t) stream));
+            return rc;
+        }
+        if ((size_t) npencil > op->zero_count) {
+            if (op->d_zero) SZB_CUDA_OK(cudaFree(op->d_zero));
+            op->d_zero = nullptr; op->zero_count = 0;
+            SZB_CUDA_OK(cudaMalloc(&op->d_zero, sizeof(double) * (size_t) npencil));
+            SZB_CUDA_OK(cudaMemset(op->d_zero, 0, sizeof(double) * (size_t) npencil));
+            op->zero_count = (size_t) npencil;
+        }
+        d_km = d_kn = op->d_zero;
+    }
+
     // zgbsv with a single right hand side per pencil: the pipelined blocked
     // shared-memory-window kernel (invert_pipe.cu).  SZB_INVERT=v1 / v2 / v3 in the
     // environment selects the generic global-memory kernel / the register-window kernel

@@ -90,6 +90,7 @@ struct AccumulateArgs {
     int nrbc;               // bit0 a, bit1 b, bit2 c
     double a[25], b[25], c[25];
     int npencil;
+    int zero_wave;          // linearize::rhome_y: the operator at km = kn = 0 for every pencil
 };
 
 // One output row of phi L at collocation point y, statically specialised on the equation
@@ -158,7 +159,7 @@ accumulate_kernel(const AccumulateArgs A)
     for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++it) {
     const int stage = it & 1;
     const cplx *s_in = s_inbuf + stage * 5 * np;
-    const double km = A.km[p], kn = A.kn[p];
+    const double km = A.zero_wave ? 0.0 : A.km[p], kn = A.zero_wave ? 0.0 : A.kn[p];
     const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
     cplx *out = A.out + slot * A.out_ps;
     if (threadIdx.x == 0 && p + (int) gridDim.x < A.npencil) fetch(p + gridDim.x, stage ^ 1);
@@ -292,6 +293,8 @@ int szb_imexop_create(const szb_bsplineop *w, szb_imexop **out)
     op->d_D = nullptr; op->d_refs = nullptr; op->d_terms = nullptr;
     op->d_work = nullptr; op->work_bytes = 0; op->work_slots = 0; op->field_ctx = nullptr;
     op->d_refine = nullptr; op->refine_bytes = 0;
+    op->d_work00 = nullptr; op->work00_bytes = 0; op->d_zero = nullptr; op->zero_count = 0;
+    op->linearization = SZB_LINEARIZE_RHOME_XYZ;
     op->have_a = op->have_b = op->have_c = false;
     std::memset(&op->iso, 0, sizeof(op->iso));
     op->iso.enforce_lower = 1; op->iso.enforce_upper = 1;
@@ -331,11 +334,19 @@ void szb_imexop_destroy(szb_imexop *op)
 {
     if (!op) return;
     if (op->field_ctx) szb::field_ctx_free(op->field_ctx);
-    cudaFree(op->d_D); cudaFree(op->d_refs); cudaFree(op->d_terms); cudaFree(op->d_work); cudaFree(op->d_refine);
+    cudaFree(op->d_D); cudaFree(op->d_refs); cudaFree(op->d_terms); cudaFree(op->d_work); cudaFree(op->d_refine); cudaFree(op->d_work00); cudaFree(op->d_zero);
     delete op;
 }
 
 szb_bsmbsm szb_imexop_bsmbsm(const szb_imexop *op) { return op->A; }
+
+int szb_imexop_set_linearization(szb_imexop *op, int linearization)
+{
+    if (!op) return -1;
+    if (linearization != SZB_LINEARIZE_RHOME_XYZ && linearization != SZB_LINEARIZE_RHOME_Y) return -2;
+    op->linearization = linearization;
+    return 0;
+}
 
 int szb_imexop_set_scenario(szb_imexop *op, const szb_rholut_imexop_scenario *s)
 {
@@ -424,6 +435,7 @@ int szb_imexop_accumulate_batch(const szb_imexop *op, const double phi[2],
     std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
     std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
     A.npencil = npencil;
+    A.zero_wave = op->linearization == SZB_LINEARIZE_RHOME_Y;
     const size_t smem = sizeof(cplx) * (10 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
     if (smem > 227 * 1024) return -1;
     int threads = (op->n + 31) / 32 * 32;

@@ -37,6 +37,8 @@ int invert_refined_dispatch(const szb_imexop *op, int aiter, int dmax, const dou
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                             int *d_iters, cudaStream_t stream);
+int invert00_dispatch(const szb_imexop *op, const double phi[2], int npencil, const int *d_index,
+                      cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info, cudaStream_t stream);
 int invert_blocked_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
@@ -104,5 +106,10 @@ struct szb_imexop {
     mutable void  *field_ctx;          // cached whole-field plan (capi.cu)
     mutable void  *d_refine;           // workspace of the refined fused invert (invert_pipe.cu)
     mutable size_t refine_bytes;
+    mutable void  *d_work00;           // rhome_y: the one factorisation, U rows, pivots (rhome_y.cu)
+    mutable size_t work00_bytes;
+    mutable double *d_zero;            // zero wavenumbers for the general kernels under rhome_y
+    mutable size_t zero_count;
+    int linearization;                 // SZB_LINEARIZE_*
     int sm_count;
 };

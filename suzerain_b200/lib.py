@@ -97,6 +97,7 @@ PROTOTYPES = {
     "szb_imexop_set_isothermal": (C.c_int, [c_void_p, C.POINTER(Isothermal)]),
     "szb_imexop_set_nrbc": (C.c_int, [c_void_p, c_double_p, c_double_p, c_double_p]),
     "szb_imexop_bsmbsm": (Bsmbsm, [c_void_p]),
+    "szb_imexop_set_linearization": (C.c_int, [c_void_p, C.c_int]),
     "szb_imexop_accumulate_batch": (C.c_int, [c_void_p, D2, C.c_int, c_void_p, c_void_p, c_void_p,
                                               c_void_p, C.c_size_t, C.c_size_t, D2,
                                               c_void_p, C.c_size_t, C.c_size_t, c_void_p]),
@@ -127,6 +128,12 @@ PROTOTYPES = {
     "szb_rholut_imexop_packf": (C.c_int, [D2, C.c_double, C.c_double, C.POINTER(Scenario),
                                           C.POINTER(Ref), C.POINTER(RefLd), c_void_p,
                                           C.POINTER(Bsmbsm), c_void_p] + [c_double_p] * 3),
+    "szb_rholut_imexop_accumulate00": (C.c_int, [D2, C.POINTER(Scenario), C.POINTER(Ref), C.POINTER(RefLd), c_void_p]
+                                       + [c_void_p] * 5 + [D2] + [c_void_p] * 5 + [c_double_p]),
+    "szb_rholut_imexop_packc00": (C.c_int, [D2, C.POINTER(Scenario), C.POINTER(Ref), C.POINTER(RefLd), c_void_p,
+                                            C.POINTER(Bsmbsm), c_void_p, c_double_p]),
+    "szb_rholut_imexop_packf00": (C.c_int, [D2, C.POINTER(Scenario), C.POINTER(Ref), C.POINTER(RefLd), c_void_p,
+                                            C.POINTER(Bsmbsm), c_void_p, c_double_p]),
     "szb_wavegrid_npencils": (C.c_int, [C.POINTER(WaveGrid)]),
     "szb_wavegrid_nactive": (C.c_int, [C.POINTER(WaveGrid)]),
     "szb_wavegrid_wavenumbers": (C.c_int, [C.POINTER(WaveGrid), c_double_p, c_double_p, c_int_p]),

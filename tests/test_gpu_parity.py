@@ -307,6 +307,79 @@ def test_golden_bsplineop_actions_on_gpu(dev):
 
 
 # ---------------------------------------------------------------------------
+# linearize::rhome_y: the wavenumber-independent "00" operator against the reference's
+# own suzerain_rholut_imexop_{accumulate,packf}00 and its rhome_y loop (oracle/_ref)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("casename", ["tiny", "ch96", "bl"])
+def test_rhome_y_accumulate_and_invert_match_reference(dev, request, casename):
+    import torch
+    import suzerain_b200 as sz
+    case = request.getfixturevalue(casename)
+    P = pc.oracle_problem(case, "ref")
+    npen = len(case.km)
+    x = case.x.reshape(npen, -1)
+    op = pc.make_imexop(case).set_linearization("rhome_y")
+    km = torch.from_numpy(case.km).to(dev)                      # ignored under rhome_y
+    kn = torch.from_numpy(case.kn).to(dev)
+    # accumulate
+    beta = 0.3 - 0.8j
+    y0 = np.random.default_rng(4).standard_normal(x.shape) + 0j
+    want = P.accumulate00(case.phi, x, beta=beta, y=y0)
+    xs = torch.from_numpy(case.x).to(dev)
+    out = torch.from_numpy(y0.reshape(case.x.shape).copy()).to(dev)
+    op.accumulate_batch(case.phi, km, kn, xs, beta, out)
+    torch.cuda.synchronize()
+    assert pc.relmax(out.cpu().numpy().reshape(npen, -1), want) <= TOL
+    # invert, both solver specifications
+    want = P.invert00(case.phi, x, want_ipiv=True)
+    assert want["info"] == 0
+    for solver in ("zgbsv", "zcgbsvx"):
+        st = torch.from_numpy(case.x.copy()).to(dev)
+        ipiv = torch.zeros((npen, op.N), dtype=torch.int32, device=dev)
+        info = torch.full((npen,), -7, dtype=torch.int32, device=dev)
+        op.invert_batch(sz.SolverSpec(method=solver), case.phi, km, kn, st, ipiv=ipiv, info=info)
+        torch.cuda.synchronize()
+        assert np.all(info.cpu().numpy() == 0)
+        assert np.array_equal(ipiv.cpu().numpy(), np.tile(want["ipiv"], (npen, 1))), "pivot choices differ"
+        assert pc.relmax(st.cpu().numpy().reshape(npen, -1), want["x"]) <= TOL
+
+
+def test_rhome_y_per_pencil_wrappers_match_reference(dev, tiny):
+    """szb_rholut_imexop_{accumulate,packc,packf}00 with the reference's signatures."""
+    from suzerain_b200 import lib as L
+    case = tiny
+    P = pc.oracle_problem(case, "ref")
+    lib = L.load()
+    op = pc.make_imexop(case)
+    n, N = case.n, 5 * case.n
+    phi2 = (C.c_double * 2)(case.phi.real, case.phi.imag)
+    scen = L.Scenario(*[case.scenario[k] for k in ("Re", "Pr", "Ma", "alpha", "gamma")])
+    refs = np.ascontiguousarray(case.refs)
+    ref = L.Ref(*[refs[i].ctypes.data_as(L.c_double_p) for i in range(26)])
+    refld = L.RefLd(*([1] * 26))
+    A = lib.szb_imexop_bsmbsm(op.handle)
+    for packf, fn in ((False, lib.szb_rholut_imexop_packc00), (True, lib.szb_rholut_imexop_packf00)):
+        rows = A.LD + (A.KL if packf else 0)
+        out = np.full((N, rows), np.nan + 1j * np.nan, dtype=np.complex128)
+        L.check("pack00", fn(phi2, C.byref(scen), C.byref(ref), C.byref(refld), case.bop.handle, C.byref(A),
+                             out.ctypes.data_as(C.c_void_p), None))
+        want = P.assemble00(case.phi, packf=packf, with_bc=False)
+        m = ~np.isnan(want)
+        assert np.array_equal(np.isnan(out), np.isnan(want))
+        assert np.abs(out[m] - want[m]).max() <= TOL * np.abs(want[m]).max()
+    x = case.x[0]
+    y = np.zeros_like(x)
+    b2 = (C.c_double * 2)(0.0, 0.0)
+    xin = [np.ascontiguousarray(x[f]) for f in range(5)]
+    yout = [np.ascontiguousarray(y[f]) for f in range(5)]
+    L.check("accumulate00", lib.szb_rholut_imexop_accumulate00(
+        phi2, C.byref(scen), C.byref(ref), C.byref(refld), case.bop.handle,
+        *[a.ctypes.data_as(C.c_void_p) for a in xin], b2, *[a.ctypes.data_as(C.c_void_p) for a in yout], None))
+    want = P.accumulate00(case.phi, x.reshape(1, -1))
+    assert pc.relmax(np.concatenate(yout).reshape(1, -1), want) <= TOL
+
+
+# ---------------------------------------------------------------------------
 # wave-space building blocks of the nonlinear operator (SURVEY 8f-1): batched B-spline operator
 # apply and diffwave against the reference's own C (oracle/_ref)
 # ---------------------------------------------------------------------------
