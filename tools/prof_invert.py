@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: one invert (+ accumulate) launch over a bounded
-number of pencils of a named grid.  python tools/prof_invert.py [config] [npencils] [solver]"""
+number of pencils of a named grid.  python tools/prof_invert.py [config] [npencils] [solver]
+(SZB_LINEARIZATION=rhome_y selects the wavenumber-independent linearisation.)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -17,6 +18,7 @@ for rep in range(2):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import suzerain_b200 as sz
     op = pc.make_imexop(case)
+    op.set_linearization(os.environ.get("SZB_LINEARIZATION", "rhome_xyz"))
     km = torch.from_numpy(case.km).to(dev); kn = torch.from_numpy(case.kn).to(dev)
     st = torch.from_numpy(case.x.copy()).to(dev)
     info = torch.zeros(len(case.km), dtype=torch.int32, device=dev)
