@@ -26,6 +26,18 @@ namespace {
 // first maximum of |re| + |im|, reciprocal pivot times column, rank-one update; a zero pivot
 // sets info and the factorisation carries on.
 constexpr int FACTOR00_AHEAD = 4;
+constexpr int FACTOR00_TASKS = 8;      // update entries per thread: kl (kl + ku) <= 8 * 512
+
+// 1/z with one division in the comfortable exponent range, Smith's algorithm outside it
+__device__ __forceinline__ cplx fast_recip(cplx z)
+{
+    const double m = fmax(fabs(z.x), fabs(z.y));
+    if (m > 1e-140 && m < 1e140) {
+        const double d = 1.0 / fma(z.x, z.x, z.y * z.y);
+        return cplx(z.x * d, -z.y * d);
+    }
+    return recip(z);
+}
 
 __global__ void __launch_bounds__(512)
 factor00_kernel(int n, int kl, int ku, cplx *ab, int ldab, int *ipiv, int *info)
@@ -35,11 +47,13 @@ factor00_kernel(int n, int kl, int ku, cplx *ab, int ldab, int *ipiv, int *info)
     __shared__ cplx s_piv, s_d0, s_rinv;
     __shared__ int s_jp, s_ok;
     const int kv = kl + ku, RC = kv + 1 + FACTOR00_AHEAD, tid = threadIdx.x, nt = blockDim.x;
-    auto col = [&](int c) { return ring + (size_t) (c % RC) * ldab; };
+    int sj = 0;                                  // ring slot of column j
+    // column j + c, 0 <= c < RC, without a division
+    auto colr = [&](int c) { int sl = sj + c; sl -= sl >= RC ? RC : 0; return ring + (size_t) sl * ldab; };
     // columns arrive by cp.async, FACTOR00_AHEAD column steps before they are first touched
-    auto load_col = [&](int c) {
+    auto load_col = [&](int c, int slot) {
         if (c < n) {
-            cplx *d = col(c); const cplx *g = ab + (size_t) c * ldab;
+            cplx *d = ring + (size_t) slot * ldab; const cplx *g = ab + (size_t) c * ldab;
             for (int r = tid; r < ldab; r += nt) {
                 if (r < kl) d[r] = cplx(0.0, 0.0);
                 else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned) __cvta_generic_to_shared(d + r)), "l"(g + r) : "memory");
@@ -47,33 +61,43 @@ factor00_kernel(int n, int kl, int ku, cplx *ab, int ldab, int *ipiv, int *info)
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    for (int c = 0; c < kv + FACTOR00_AHEAD; ++c) load_col(c);
+    for (int c = 0; c < kv + FACTOR00_AHEAD; ++c) load_col(c, c);
     int ju = 0, inf = 0;
     for (int j = 0; j < n; ++j) {
         const int km = min(kl, n - 1 - j);
-        cplx *cj = col(j);
+        cplx *cj = ring + (size_t) sj * ldab;
         // column j + kv (the last one this step can touch) has landed for every thread, and
         // column j - 1 has left: its slot takes the next request
         asm volatile("cp.async.wait_group %0;" :: "n"(FACTOR00_AHEAD - 1) : "memory");
         __syncthreads();
-        load_col(j + kv + FACTOR00_AHEAD);
+        load_col(j + kv + FACTOR00_AHEAD, sj == 0 ? RC - 1 : sj - 1);
         if (tid < 32) {
             double best = -1.0; int bi = 0;
             for (int i = tid; i <= km; i += 32) {
                 const double m = cabs1(cj[kv + i]);
                 if (m > best) { best = m; bi = i; }
             }
+            // the top word of the magnitudes decides almost every column with one REDUX; lanes
+            // that share the largest top word settle it exactly
+            const unsigned key = best < 0.0 ? 0u : (unsigned) __double2hiint(best) + 1u;
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+            unsigned tie = __ballot_sync(0xffffffffu, key == kmax);
+            if (tie & (tie - 1)) {
+                if (key != kmax) best = -1.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                tie = (tid == (bi & 31)) ? 1u << tid : 0u;
+                tie = __ballot_sync(0xffffffffu, tie != 0);
             }
-            if (tid == 0) {
+            if (tid == __ffs(tie) - 1) {
                 const cplx pv = cj[kv + bi];
                 s_jp = bi; s_piv = pv; s_d0 = cj[kv];
                 s_ok = (pv.x != 0.0 || pv.y != 0.0);
-                if (s_ok) s_rinv = recip(pv);
+                if (s_ok) s_rinv = fast_recip(pv);
                 ipiv[j] = j + bi + 1;
             }
         }
@@ -87,7 +111,7 @@ factor00_kernel(int n, int kl, int ku, cplx *ab, int ldab, int *ipiv, int *info)
                 if (jp) {
                     if (tid == 0) cj[kv] = s_piv;
                     else {
-                        cplx *cc = col(j + tid);
+                        cplx *cc = colr(tid);
                         const cplx a = cc[kv - tid], b = cc[kv + jp - tid];
                         cc[kv - tid] = b; cc[kv + jp - tid] = a;
                     }
@@ -98,21 +122,31 @@ factor00_kernel(int n, int kl, int ku, cplx *ab, int ldab, int *ipiv, int *info)
                 cj[kv + i] = v * s_rinv;
             }
             __syncthreads();
-            // rank-one update of columns j+1 .. ju
+            // rank-one update of columns j+1 .. ju: loads first, stores last
             const int total = km * nc;
-            for (int e = tid; e < total; e += nt) {
-                const int c = e / km + 1, i = e - (c - 1) * km + 1;
-                cplx *cc = col(j + c);
-                cplx w = cc[kv + i - c];
-                submul(w, cj[kv + i], cc[kv - c]);
-                cc[kv + i - c] = w;
+            const float rkm = 1.0f / (float) km;
+            cplx *pw[FACTOR00_TASKS]; cplx w[FACTOR00_TASKS];
+#pragma unroll
+            for (int t = 0; t < FACTOR00_TASKS; ++t) {
+                const int e = tid + t * 512;
+                pw[t] = nullptr;
+                if (e < total) {
+                    const int c0 = __float2int_rz(((float) e + 0.5f) * rkm), c = c0 + 1, i = e - c0 * km + 1;
+                    cplx *cc = colr(c);
+                    pw[t] = cc + kv + i - c;
+                    w[t] = *pw[t];
+                    submul(w[t], cj[kv + i], cc[kv - c]);
+                }
             }
+#pragma unroll
+            for (int t = 0; t < FACTOR00_TASKS; ++t) if (pw[t]) *pw[t] = w[t];
         } else if (!inf) inf = j + 1;
         // column j is final: write it back; the column that enters next takes a free slot
         {
             cplx *g = ab + (size_t) j * ldab;
             for (int r = tid; r < ldab; r += nt) g[r] = cj[r];
         }
+        sj = sj + 1 == RC ? 0 : sj + 1;
     }
     if (tid == 0) *info = inf;
 }
@@ -583,7 +617,7 @@ int invert00_dispatch(const szb_imexop *op, const double phi[2], int npencil, co
                       cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info, cudaStream_t stream)
 {
     const int N = op->A.N, KL = op->A.KL, KU = op->A.KU, ldab = op->A.LD + KL, kv = KL + KU;
-    if (kv + 3 > FWR || KL > BWR || kv >= 128) return -1;
+    if (kv + 3 > FWR || KL > BWR || kv >= 128 || KL * kv > FACTOR00_TASKS * 512) return -1;
     const int nblk = (N + 3) / 4;
     // workspace: LU | regrouped factors | ipiv | info | zero wavenumbers | plain flags
     const size_t b_lu = sizeof(cplx) * (size_t) ldab * N;
