@@ -143,12 +143,19 @@ typedef struct szb_isothermal {
 
 /* Solver specification.  Replaces specification_zgbsv
  * (suzerain/specification_zgbsv.cpp:46-124). */
-enum { SZB_SOLVER_ZGBSV = 0, SZB_SOLVER_ZCGBSVX = 1 };
+enum { SZB_SOLVER_ZGBSV = 0, SZB_SOLVER_ZCGBSVX = 1, SZB_SOLVER_ZGBSVX = 2 };
 typedef struct szb_zgbsv_spec {
     int    method;   /* SZB_SOLVER_*                                   */
     int    aiter;    /* zcgbsvx: iterations before stagnation test (1)  */
     int    diter;    /* zcgbsvx: max double-precision refinements  (5)  */
     double tolsc;    /* zcgbsvx: 0 => absolute eps tolerance       (0)  */
+    int    equil;    /* zgbsvx: equilibrate (FACT = 'E')           (0)  */
+    int    reuse;    /* zcgbsvx: a HINT here -- every pencil is factored
+                      * afresh on the device (the reference reuses the
+                      * previous wavenumber's factors as a preconditioner
+                      * and refines to the same criterion)          (0)  */
+    int    siter;    /* zcgbsvx: a HINT here -- no single-precision
+                      * factorisation is attempted                  (-1) */
 } szb_zgbsv_spec;
 szb_zgbsv_spec szb_zgbsv_spec_default(void);        /* zcgbsvx defaults */
 

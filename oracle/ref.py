@@ -172,6 +172,31 @@ class Problem:
             res["iters"] = iters
         return res
 
+    def invert_spec(self, phi: complex, km, kn, state, method="zcgbsvx", equil=False, reuse=False,
+                    aiter=1, siter=-1, diter=5, tolsc=0.0, rowlen=1, nthreads=1):
+        """Any solver specification of apps/perfect/test_implicit_solvers.sh:24-30, with the
+        solver state carried along rows of ``rowlen`` consecutive pencils as the reference's
+        kx loop does (so that reuse=true takes its approximate-factorisation path)."""
+        km = np.ascontiguousarray(km, dtype=np.float64)
+        kn = np.ascontiguousarray(kn, dtype=np.float64)
+        x = np.array(state, dtype=np.complex128, order="C", copy=True)
+        npencil = x.shape[0]
+        assert x.shape == (npencil, self.N) and km.shape == (npencil,) == kn.shape
+        iters = np.zeros((npencil, 2), dtype=np.int32)
+        stats = np.zeros((npencil, 2), dtype=np.float64)
+        bad = C.c_int(-1)
+        phi2 = (C.c_double * 2)(complex(phi).real, complex(phi).imag)
+        a, b, c = self._abc()
+        assert self.bc is not None
+        f = lib().ref_invert_spec_batch
+        f.restype = C.c_int
+        info = f(C.c_int({"zgbsv": 0, "zcgbsvx": 1, "zgbsvx": 2}[method]), C.c_int(int(equil)), C.c_int(int(reuse)),
+                 C.c_int(aiter), C.c_int(siter), C.c_int(diter), C.c_double(tolsc), phi2,
+                 C.byref(self.scen), C.byref(self.ref), C.byref(self.refld), C.byref(self.w),
+                 C.byref(self.bc), a, b, c, C.c_int(npencil), C.c_int(rowlen), _p(km), _p(kn),
+                 x.ctypes.data_as(C.c_void_p), _p(iters, C.c_int), _p(stats), C.c_int(int(nthreads)), C.byref(bad))
+        return {"x": x, "info": info, "first_bad": bad.value, "iters": iters, "stats": stats}
+
     def accumulate(self, phi: complex, km, kn, x, beta: complex = 0.0, y=None, nthreads=1):
         km = np.ascontiguousarray(km, dtype=np.float64)
         kn = np.ascontiguousarray(kn, dtype=np.float64)

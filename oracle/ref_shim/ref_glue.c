@@ -249,6 +249,115 @@ int ref_invert_batch(int solver, const double phi[2],
     return rc;
 }
 
+/* ---- invert loop body for every solver specification of
+ * apps/perfect/test_implicit_solvers.sh:24-30 ----
+ * method: 0 zgbsv, 1 zcgbsvx, 2 zgbsvx (specification_zgbsv.cpp).  The pencils are taken
+ * in rows of rowlen consecutive ones (one kz row of operator_hybrid_isothermal.cpp:613-688):
+ * inside a row they are solved sequentially with the solver state (fact_, apprx_) carried
+ * from one to the next exactly as bsmbsm_solver::{supplied_PAPT,apprx,solve} do
+ * (bsmbsm_solver.cpp:80-102), so that reuse=true exercises the reference's
+ * approximate-factorisation path; rows are independent (apprx(false) at :622).
+ * iters_out: zcgbsvx diter / siter pairs (2 ints per pencil); stats_out (may be NULL):
+ * per pencil {refactored?, berr or res}. */
+int ref_invert_spec_batch(int method, int equil, int reuse, int aiter, int siter0, int diter0,
+                          double tolsc0, const double phi[2],
+                          const suzerain_rholut_imexop_scenario *s,
+                          const suzerain_rholut_imexop_ref *r,
+                          const suzerain_rholut_imexop_refld *ld,
+                          const suzerain_bsplineop_workspace *w,
+                          const ref_bc *bc,
+                          const double *a, const double *b, const double *c,
+                          int npencil, int rowlen, const double *km, const double *kn,
+                          complex_double *state, int *iters_out, double *stats_out,
+                          int nthreads, int *first_bad)
+{
+    const suzerain_bsmbsm A0 = suzerain_bsmbsm_construct(5, w->n, w->max_kl, w->max_ku);
+    const complex_double cphi = phi[0] + _Complex_I*phi[1];
+    int rc = 0, bad = -1;
+    if (nthreads < 1) nthreads = 1;
+    if (rowlen < 1) rowlen = 1;
+    const int nrows = (npencil + rowlen - 1)/rowlen;
+    const char default_fact = (method == 2 && equil) ? 'E' : 'N';
+
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        suzerain_bsmbsm A = A0;
+        const int N = A.N, ldlu = A.KL + A.LD;
+        const int nbuf = A.ld*A.n > 75 ? A.ld*A.n : 75;
+        complex_double *buf  = (complex_double *) malloc(nbuf*sizeof(*buf));
+        complex_double *LU   = (complex_double *) malloc((size_t) ldlu*N*sizeof(*LU));
+        complex_double *PAPT = (complex_double *) malloc((size_t) A.LD*N*sizeof(*PAPT));
+        complex_double *PB   = (complex_double *) malloc(N*sizeof(*PB));
+        complex_double *PX   = (complex_double *) malloc(N*sizeof(*PX));
+        complex_double *R    = (complex_double *) malloc(2*(size_t) N*sizeof(*R));
+        double         *rcw  = (double *) malloc(3*(size_t) N*sizeof(double));
+        int            *ipiv = (int *) malloc(N*sizeof(int));
+
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int row = 0; row < nrows; ++row) {
+            char fact = default_fact, equed = 'N';
+            int apprx = 0;
+            double afrob = -1;
+            /* "Factorization reuse will not aid us across large jumps in km" (:622) */
+            for (int p = row*rowlen; p < npencil && p < (row + 1)*rowlen; ++p) {
+                complex_double * const x = state + (size_t) p*N;
+                int info = 0;
+                if (method == 0) {
+                    suzerain_rholut_imexop_packf(cphi, km[p], kn[p], s, r, ld, w,
+                            0, 1, 2, 3, 4, buf, &A, LU, a, b, c);
+                    enforcer_op(&A, bc, LU + A.KL, ldlu);
+                } else {
+                    suzerain_rholut_imexop_packc(cphi, km[p], kn[p], s, r, ld, w,
+                            0, 1, 2, 3, 4, buf, &A, PAPT, a, b, c);
+                    enforcer_op(&A, bc, PAPT, A.LD);
+                }
+                /* supplied_PAPT() */
+                if (method == 1) afrob = -1;
+                if (reuse) apprx = fact != default_fact; else fact = default_fact;
+                suzerain_bsmbsm_zaPxpby('N', A.S, A.n, 1, x, 1, 0, PB, 1);
+                enforcer_rhs(&A, bc, PB);
+                if (method == 0) {
+                    info = suzerain_lapack_zgbtrf(N, N, A.KL, A.KU, LU, ldlu, ipiv);
+                    if (!info) info = suzerain_lapack_zgbtrs('T', N, A.KL, A.KU, 1, LU, ldlu, ipiv, PB, N);
+                    if (!info) suzerain_bsmbsm_zaPxpby('T', A.S, A.n, 1, PB, 1, 0, x, 1);
+                } else if (method == 2) {
+                    double rcond = 0, ferr = 0, berr = 0;
+                    info = suzerain_lapack_zgbsvx(fact, 'T', N, A.KL, A.KU, 1, PAPT, A.LD, LU, ldlu,
+                            ipiv, &equed, rcw, rcw + N, PB, N, PX, N, &rcond, &ferr, &berr, R, rcw + 2*N);
+                    fact = 'F';
+                    if (!info) suzerain_bsmbsm_zaPxpby('T', A.S, A.n, 1, PX, 1, 0, x, 1);
+                    if (stats_out) {
+                        stats_out[2*p] = (equed == 'R' || equed == 'B') + 2*(equed == 'C' || equed == 'B');
+                        stats_out[2*p + 1] = berr;
+                    }
+                } else {
+                    int siter = siter0, diter = diter0;
+                    double tolsc = tolsc0, res = 0;
+                    info = suzerain_lapackext_zcgbsvx(&fact, &apprx, aiter, 'T',
+                            N, A.KL, A.KU, PAPT, &afrob, LU, ipiv, PB, PX,
+                            &siter, &diter, &tolsc, R, &res);
+                    if (!info) suzerain_bsmbsm_zaPxpby('T', A.S, A.n, 1, PX, 1, 0, x, 1);
+                    if (iters_out) { iters_out[2*p] = diter; iters_out[2*p + 1] = siter; }
+                    if (stats_out) { stats_out[2*p] = apprx; stats_out[2*p + 1] = res; }
+                }
+                if (info) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+                    if (bad < 0 || p < bad) { bad = p; rc = info; }
+                }
+            }
+        }
+        free(buf); free(LU); free(PAPT); free(PB); free(PX); free(R); free(rcw); free(ipiv);
+    }
+    if (first_bad) *first_bad = bad;
+    return rc;
+}
+
 /* ---- accumulate loop body over a batch of active pencils ----
  * in/out: npencil pencils of 5*n complex each, field stride n. */
 void ref_accumulate_batch(const double phi[2],

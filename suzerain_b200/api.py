@@ -138,40 +138,65 @@ def htstretch_breakpoints(ndof, k, left, right, htdelta):
     return (right - left) * b + left
 
 
+def _parse_bool(text):
+    t = text.strip().lower()
+    if t in ("true", "1"):
+        return True
+    if t in ("false", "0"):
+        return False
+    raise ValueError(f"not a boolean: {text!r}")
+
+
 @dataclasses.dataclass
 class SolverSpec:
-    """specification_zgbsv (suzerain/specification_zgbsv.cpp:46-124)."""
+    """specification_zgbsv (suzerain/specification_zgbsv.cpp:46-124).
+
+    ``reuse`` and ``siter`` are accepted for drop-in compatibility and are hints on the
+    device: every pencil is factored afresh in double precision and refined to the same
+    stopping criterion (the reference's own test holds the variants to 6e-15 of each other,
+    apps/perfect/test_implicit_solvers.sh:24-50)."""
     method: str = "zcgbsvx"
     aiter: int = 1
     diter: int = 5
     tolsc: float = 0.0
+    equil: bool = False
+    reuse: bool = False
+    siter: int = -1
 
     @classmethod
     def parse(cls, text: str):
-        """Accepts the reference grammar subset: zgbsv | zcgbsvx[,aiter=i,diter=i,tolsc=d]."""
-        parts = [p.strip() for p in text.split(",") if p.strip()]
-        if not parts or parts[0] not in ("zgbsv", "zcgbsvx"):
-            raise ValueError(f"unsupported solver specification {text!r}")
-        spec = cls(method=parts[0])
+        """The reference grammar: zgbsv | zgbsvx[,equil=b] | zcgbsvx[,reuse=b][,aiter=i][,siter=i]
+        [,diter=i][,tolsc=d]; case-insensitive, whitespace ignored, empty = defaults."""
+        parts = [p.strip() for p in text.split(",")]
+        if parts == [""]:
+            return cls()
+        head = parts[0].lower()
+        if head not in ("zgbsv", "zgbsvx", "zcgbsvx") or any(p == "" for p in parts):
+            raise ValueError(f"spec_zgbsv specification {text!r} invalid")
+        spec = cls(method=head)
+        allowed = {"zgbsv": (), "zgbsvx": ("equil",), "zcgbsvx": ("reuse", "aiter", "siter", "diter", "tolsc")}[head]
+        seen = set()
         for kv in parts[1:]:
-            key, _, val = kv.partition("=")
-            key = key.strip()
-            if spec.method != "zcgbsvx" or key not in ("aiter", "diter", "tolsc", "reuse", "siter"):
-                raise ValueError(f"unknown option {kv!r} in {text!r}")
-            if key == "tolsc":
+            key, eq, val = kv.partition("=")
+            key = key.strip().lower()
+            if not eq or key not in allowed or key in seen:
+                raise ValueError(f"spec_zgbsv specification {text!r} invalid beginning with {kv!r}")
+            seen.add(key)
+            if key in ("equil", "reuse"):
+                setattr(spec, key, _parse_bool(val))
+            elif key == "tolsc":
                 spec.tolsc = float(val)
-            elif key == "aiter":
-                spec.aiter = int(val)
-            elif key == "diter":
-                spec.diter = int(val)
-            elif key == "reuse" and val.strip().lower() not in ("0", "false", "no"):
-                raise ValueError("reuse=true is not supported")
-            elif key == "siter" and int(val) >= 0:
-                raise ValueError("single-precision refinement (siter>=0) is not supported")
+            else:
+                setattr(spec, key, int(val))
         return spec
 
+    def in_place(self):
+        """specification_zgbsv::in_place (specification_zgbsv.cpp:116-124)."""
+        return self.method == "zgbsv"
+
     def c(self):
-        return _L.ZgbsvSpec({"zgbsv": 0, "zcgbsvx": 1}[self.method], self.aiter, self.diter, self.tolsc)
+        return _L.ZgbsvSpec({"zgbsv": 0, "zcgbsvx": 1, "zgbsvx": 2}[self.method], self.aiter, self.diter,
+                            self.tolsc, int(self.equil), int(self.reuse), self.siter)
 
 
 class ImexOp:

@@ -151,6 +151,144 @@ __device__ inline int zcgbsvx_cta(char trans, int n, int kl, int ku, int aiter, 
     return info;
 }
 
+// CTA-wide max / min over threads of a double; result to all threads.
+__device__ inline double cta_max(double v, double *s_red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[w] = v;
+    __syncthreads();
+    double t = s_red[0];
+    for (int i = 1; i < nw; ++i) t = fmax(t, s_red[i]);
+    return t;
+}
+__device__ inline double cta_min(double v, double *s_red) { return -cta_max(-v, s_red); }
+
+// ---------------------------------------------------------------------------
+// zgbsvx (LAPACK expert driver) for TRANS = 'T' and one right hand side, as
+// bsmbsm_solver_zgbsvx::solve_hook calls it (suzerain/bsmbsm_solver.cpp:253-289) with
+// FACT = 'E' (spec equil=true) or 'N': optional equilibration (zgbequ + zlaqgb, which
+// scales ab in place), zgbtrf, zgbtrs, then zgbrfs: componentwise-backward-error
+// refinement, at most ITMAX = 5 corrections, stopping once berr <= eps or berr no longer
+// halves.  The solution is unscaled by the row factors afterwards.  rcond / ferr (zgbcon,
+// zlacn2) are statistics of the reference's log and are not produced here.
+// equed: bit 0 row scaling, bit 1 column scaling (kept across right hand sides).
+// ---------------------------------------------------------------------------
+__device__ inline int zgbsvx_cta(bool equil, int n, int kl, int ku, cplx *ab, cplx *afb, int *ipiv,
+                                 cplx *b, cplx *x, cplx *r, double *rw, double *rs, double *cs,
+                                 bool &factored, int &equed, int *count_out, double *berr_out,
+                                 const LuScratch S, double *s_red)
+{
+    const int ldab = kl + 1 + ku, ldafb = 2 * kl + 1 + ku;
+    const double eps = DBL_EPSILON * 0.5, safmin = DBL_MIN;          // dlamch('E'), dlamch('S')
+    int info = 0;
+    if (!factored) {
+        equed = 0;
+        if (equil) {
+            const double smlnum = safmin, bignum = 1.0 / smlnum;
+            // zgbequ: r_i = 1 / max_j |a_ij|, c_j = 1 / max_i r_i |a_ij|  (|.| = |re| + |im|)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                double m = 0.0;
+                for (int j = max(0, i - kl); j <= min(n - 1, i + ku); ++j)
+                    m = fmax(m, cabs1(ab[(size_t) j * ldab + ku + i - j]));
+                rs[i] = m;
+            }
+            __syncthreads();
+            double lmax = 0.0, lmin = bignum;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) { lmax = fmax(lmax, rs[i]); lmin = fmin(lmin, rs[i]); }
+            const double rcmax = cta_max(lmax, s_red), rcmin = cta_min(lmin, s_red);
+            const double amax = rcmax;
+            bool ok = rcmin != 0.0;
+            double rowcnd = 0.0, colcnd = 0.0;
+            if (ok) {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) rs[i] = 1.0 / fmin(fmax(rs[i], smlnum), bignum);
+                rowcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+                __syncthreads();
+                for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                    double m = 0.0;
+                    for (int i = max(0, j - ku); i <= min(n - 1, j + kl); ++i)
+                        m = fmax(m, cabs1(ab[(size_t) j * ldab + ku + i - j]) * rs[i]);
+                    cs[j] = m;
+                }
+                __syncthreads();
+                lmax = 0.0; lmin = bignum;
+                for (int j = threadIdx.x; j < n; j += blockDim.x) { lmax = fmax(lmax, cs[j]); lmin = fmin(lmin, cs[j]); }
+                const double ccmax = cta_max(lmax, s_red), ccmin = cta_min(lmin, s_red);
+                ok = ccmin != 0.0;
+                if (ok) {
+                    for (int j = threadIdx.x; j < n; j += blockDim.x) cs[j] = 1.0 / fmin(fmax(cs[j], smlnum), bignum);
+                    colcnd = fmax(ccmin, smlnum) / fmin(ccmax, bignum);
+                }
+            }
+            __syncthreads();
+            if (ok) {
+                // zlaqgb
+                const double small = safmin / DBL_EPSILON, large = 1.0 / small, thresh = 0.1;
+                const bool rowsc = !(rowcnd >= thresh && amax >= small && amax <= large);
+                const bool colsc = !(colcnd >= thresh);
+                equed = (rowsc ? 1 : 0) | (colsc ? 2 : 0);
+                if (equed)
+                    for (int e = threadIdx.x; e < n * ldab; e += blockDim.x) {
+                        const int j = e / ldab, rr = e - j * ldab, i = j - ku + rr;
+                        if (i >= 0 && i < n) {
+                            const double f = (rowsc ? rs[i] : 1.0) * (colsc ? cs[j] : 1.0);
+                            ab[e] = ab[e] * (colsc && rowsc ? cs[j] * rs[i] : f);
+                        }
+                    }
+                __syncthreads();
+            }
+        }
+        for (int e = threadIdx.x; e < n * ldab; e += blockDim.x) {    // zlacpy
+            const int j = e / ldab, rr = e - j * ldab;
+            afb[(size_t) j * ldafb + kl + rr] = ab[e];
+        }
+        __syncthreads();
+        info = gbtrf_cta(n, kl, ku, afb, ldafb, ipiv, S);
+        factored = true;
+        if (info > 0) { *count_out = 0; *berr_out = 0.0; return info; }
+    }
+    // TRANS = 'T': the right hand side takes the column factors, the solution the row factors
+    if (equed & 2) for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] = b[i] * cs[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = b[i];
+    __syncthreads();
+    if (threadIdx.x < 32) gbtrs_T_warp(n, kl, ku, afb, ldafb, ipiv, x);
+    __syncthreads();
+    // zgbrfs
+    const int nz = min(kl + ku + 2, n + 1);
+    const double safe1 = nz * safmin, safe2 = safe1 / eps;
+    int count = 1;
+    double lstres = 3.0, berr = 0.0;
+    for (;;) {
+        gb_residual_cta('T', n, kl, ku, ab, ldab, x, b, r);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            double sum = 0.0;
+            const cplx *col = ab + (size_t) k * ldab + (ku - k);
+            for (int i = max(0, k - ku); i <= min(n - 1, k + kl); ++i) sum += cabs1(col[i]) * cabs1(x[i]);
+            rw[k] = cabs1(b[k]) + sum;
+        }
+        __syncthreads();
+        double sm = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+            sm = fmax(sm, rw[i] > safe2 ? cabs1(r[i]) / rw[i] : (cabs1(r[i]) + safe1) / (rw[i] + safe1));
+        berr = cta_max(sm, s_red);
+        if (berr > eps && 2.0 * berr <= lstres && count <= 5) {
+            if (threadIdx.x < 32) gbtrs_T_warp(n, kl, ku, afb, ldafb, ipiv, r);
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] += r[i];
+            __syncthreads();
+            lstres = berr;
+            ++count;
+        } else break;
+    }
+    if (equed & 1) for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = x[i] * rs[i];
+    __syncthreads();
+    *count_out = count - 1; *berr_out = berr;
+    return info;
+}
+
 __global__ void __launch_bounds__(256)
 zcgbsvx_batch_kernel(char trans, int n, int kl, int ku, int aiter, int dmax, double tolsc,
                      const cplx *ab, size_t stride_ab, cplx *afb, size_t stride_afb,
@@ -202,7 +340,7 @@ __global__ void zaPxpby_kernel(int transT, int S, int n, cplx alpha, const cplx 
 // ---------------------------------------------------------------------------
 struct InvertArgs {
     PackArgs pk;
-    int method, aiter, diter; double tolsc;
+    int method, aiter, diter, equil; double tolsc;
     int npencil; const int *index;
     cplx *state; size_t fs, ps;
     int nextra; cplx *extra;
@@ -229,10 +367,11 @@ invert_kernel(const InvertArgs A)
     cplx *LU = reinterpret_cast<cplx *>(slot);
     size_t off = align16(sizeof(cplx) * (size_t) ldlu * N);
     cplx *PAPT = reinterpret_cast<cplx *>(slot + off);
-    if (A.method == SZB_SOLVER_ZCGBSVX) off += align16(sizeof(cplx) * (size_t) LD * N);
+    if (A.method != SZB_SOLVER_ZGBSV) off += align16(sizeof(cplx) * (size_t) LD * N);
     cplx *vb = reinterpret_cast<cplx *>(slot + off); off += sizeof(cplx) * (size_t) N;
     cplx *vx = reinterpret_cast<cplx *>(slot + off); off += sizeof(cplx) * (size_t) N;
     cplx *vr = reinterpret_cast<cplx *>(slot + off); off += sizeof(cplx) * (size_t) N;
+    double *rw = reinterpret_cast<double *>(slot + off); off += 3 * sizeof(double) * (size_t) N;   // zgbsvx: rwork, r, c
     int *ipiv = reinterpret_cast<int *>(slot + off);
 
     for (int p = blockIdx.x; p < A.npencil; p += gridDim.x) {
@@ -240,7 +379,7 @@ invert_kernel(const InvertArgs A)
         if (A.method == SZB_SOLVER_ZGBSV) pack_pencil(K, ldlu, km, kn, s_alpha, s_x75, LU + KL);
         else                              pack_pencil(K, LD,   km, kn, s_alpha, s_x75, PAPT);
 
-        int info = 0, diter = 0;
+        int info = 0, diter = 0, equed = 0;
         bool factored = false;
         for (int rhs = 0; rhs <= A.nextra && info == 0; ++rhs) {
             cplx *v = rhs == 0 ? A.state + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps
@@ -263,6 +402,12 @@ invert_kernel(const InvertArgs A)
                 if (!factored) { info = gbtrf_cta(N, KL, KU, LU, ldlu, ipiv, S); factored = true; }
                 if (info == 0 && threadIdx.x < 32) gbtrs_T_warp(N, KL, KU, LU, ldlu, ipiv, vb);
                 sol = vb;
+            } else if (A.method == SZB_SOLVER_ZGBSVX) {
+                double berr; int it;
+                info = zgbsvx_cta(A.equil != 0, N, KL, KU, PAPT, LU, ipiv, vb, vx, vr, rw, rw + N, rw + 2 * N,
+                                  factored, equed, &it, &berr, S, s_red);
+                if (rhs == 0) diter = it;
+                sol = vx;
             } else {
                 double res; int it;
                 info = zcgbsvx_cta('T', N, KL, KU, A.aiter, A.diter, A.tolsc, PAPT, LU, ipiv,
@@ -434,8 +579,8 @@ static size_t invert_slot_bytes(const szb_imexop *op, int method)
 {
     const size_t N = op->A.N, ldlu = op->A.LD + op->A.KL;
     size_t b = (sizeof(cplx) * ldlu * N + 15) & ~(size_t) 15;
-    if (method == SZB_SOLVER_ZCGBSVX) b += (sizeof(cplx) * (size_t) op->A.LD * N + 15) & ~(size_t) 15;
-    b += 3 * sizeof(cplx) * N + sizeof(int) * N;
+    if (method != SZB_SOLVER_ZGBSV) b += (sizeof(cplx) * (size_t) op->A.LD * N + 15) & ~(size_t) 15;
+    b += 3 * sizeof(cplx) * N + 3 * sizeof(double) * N + sizeof(int) * N;
     return (b + 255) & ~(size_t) 255;
 }
 
@@ -449,7 +594,7 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
         void *stream)
 {
     if (!op) return -1;
-    if (!spec || (spec->method != SZB_SOLVER_ZGBSV && spec->method != SZB_SOLVER_ZCGBSVX)) return -2;
+    if (!spec || spec->method < SZB_SOLVER_ZGBSV || spec->method > SZB_SOLVER_ZGBSVX) return -2;
     if (!phi) return -3;
     if (npencil < 0) return -4;
     if (!d_km) return -5;
@@ -519,6 +664,7 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     InvertArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
     A.method = spec->method; A.aiter = spec->aiter; A.diter = spec->diter; A.tolsc = spec->tolsc;
+    A.equil = spec->equil;
     A.npencil = npencil; A.index = d_index;
     A.state = reinterpret_cast<cplx *>(d_state); A.fs = field_stride; A.ps = pencil_stride;
     A.nextra = nextra; A.extra = reinterpret_cast<cplx *>(d_extra);

@@ -277,6 +277,7 @@ szb_zgbsv_spec szb_zgbsv_spec_default(void)
 {
     szb_zgbsv_spec s;
     s.method = SZB_SOLVER_ZCGBSVX; s.aiter = 1; s.diter = 5; s.tolsc = 0.0;
+    s.equil = 0; s.reuse = 0; s.siter = -1;
     return s;
 }
 

@@ -46,7 +46,7 @@ class Isothermal(C.Structure):
 
 class ZgbsvSpec(C.Structure):
     _fields_ = [("method", C.c_int), ("aiter", C.c_int), ("diter", C.c_int),
-                ("tolsc", C.c_double)]
+                ("tolsc", C.c_double), ("equil", C.c_int), ("reuse", C.c_int), ("siter", C.c_int)]
 
 
 class WaveGrid(C.Structure):

@@ -592,3 +592,60 @@ def test_full_grid_properties(dev):
     got = sx.cpu().numpy().reshape(H.npencil, -1)[H.h_active[sel]]
     assert pc.relmax(got, want["x"]) <= TOL
     assert np.array_equal(ipiv.cpu().numpy()[sel], want["ipiv"])
+
+
+# ---------------------------------------------------------------------------
+# The remaining solver specifications of apps/perfect/test_implicit_solvers.sh:24-30
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("casename,scale,equil", [("tiny", 1, False), ("tiny", 1, True), ("tiny", 100, True),
+                                                  ("tiny", 1000, True), ("ch96", 1, False), ("ch96", 1000, True),
+                                                  ("bl", 1, False), ("bl", 100, True)])
+def test_zgbsvx_matches_lapack_expert_driver(dev, request, casename, scale, equil):
+    """zgbsvx[,equil=b]: LAPACK's expert driver as the reference calls it (bsmbsm_solver.cpp:253-289).
+    Scaling phi by 100 / 1000 makes zlaqgb choose row / row-and-column equilibration."""
+    import dataclasses
+    import suzerain_b200 as sz
+    base = request.getfixturevalue(casename)
+    case = dataclasses.replace(base, phi=base.phi * scale)
+    npen = len(case.km)
+    P = pc.oracle_problem(case, "ref")
+    want = P.invert_spec(case.phi, case.km, case.kn, case.x.reshape(npen, -1), method="zgbsvx", equil=equil)
+    assert want["info"] == 0
+    equed = set(want["stats"][:, 0].astype(int).tolist())
+    if casename == "tiny":
+        assert equed == ({0} if scale == 1 else {1} if scale == 100 else {3}), equed
+    got = pc.gpu_invert(case, "zgbsvx", dev, spec=sz.SolverSpec(method="zgbsvx", equil=equil))
+    assert np.all(got["info"] == 0)
+    assert pc.relmax(got["x"], want["x"]) <= TOL
+    # and the plain zgbsv pivots when nothing was scaled (same factorisation)
+    if equed == {0}:
+        ref = pc.oracle_invert(case, "zgbsv")
+        assert np.array_equal(got["ipiv"], ref["ipiv"])
+
+
+@pytest.mark.parametrize("text", ["zcgbsvx,reuse=true,aiter=1,siter=-1,diter=5,tolsc=0",
+                                  "zcgbsvx,reuse=true,aiter=5,siter=25,diter=5,tolsc=0"])
+def test_reuse_and_siter_hints_stay_within_the_reference_chain(dev, text):
+    """reuse=true / siter>=0 are hints on the device.  The reference, carrying its factorisation
+    along a kx row as a preconditioner (and trying single precision first), refines to the same
+    stopping criterion; its own test holds all variants to 6e-15 of each other in the restart
+    fields.  Here: two full kx rows of the channel grid, reference chain vs device."""
+    import dataclasses
+    import suzerain_b200 as sz
+    full = pc.make_case("channel_192x96x192")
+    rowlen = 96
+    assert np.ptp(full.kn[:rowlen]) == 0.0 and full.kn[rowlen] != full.kn[0]      # kx inner, kz outer
+    case = dataclasses.replace(full, km=full.km[:2 * rowlen], kn=full.kn[:2 * rowlen], x=full.x[:2 * rowlen])
+    spec = sz.SolverSpec.parse(text)
+    P = pc.oracle_problem(case, "ref")
+    x = case.x.reshape(2 * rowlen, -1)
+    want = P.invert_spec(case.phi, case.km, case.kn, x, method="zcgbsvx", reuse=spec.reuse, aiter=spec.aiter,
+                         siter=spec.siter, diter=spec.diter, tolsc=spec.tolsc, rowlen=rowlen, nthreads=2)
+    assert want["info"] == 0
+    assert want["stats"][:, 0].sum() > 0, "the reference never took its approximate-factorisation path"
+    got = pc.gpu_invert(case, "zcgbsvx", dev, spec=spec)
+    assert np.all(got["info"] == 0)
+    assert pc.relmax(got["x"], want["x"]) <= 5e-12
+    # per pencil, the device result satisfies the system at least as well as the reference chain's
+    fresh = P.invert_spec(case.phi, case.km, case.kn, x, method="zcgbsvx", rowlen=1, nthreads=2)
+    assert pc.relmax(got["x"], fresh["x"]) <= TOL

@@ -243,7 +243,24 @@ def test_solver_spec_grammar():
     assert sz.SolverSpec.parse("zgbsv").method == "zgbsv"
     s = sz.SolverSpec.parse("zcgbsvx,reuse=false,aiter=2,siter=-1,diter=7,tolsc=0.5")
     assert (s.aiter, s.diter, s.tolsc) == (2, 7, 0.5)
-    for bad in ("zgbsvx", "zgbsv,equil=true", "zcgbsvx,reuse=true", "zcgbsvx,siter=3", "dgbsv", ""):
+    c = sz.lib.load().szb_zgbsv_spec_default()
+    assert (c.equil, c.reuse, c.siter) == (0, 0, -1)
+    # the six specifications of apps/perfect/test_implicit_solvers.sh:24-30
+    for text, want in (("zgbsv", ("zgbsv", False, False, 1, -1, 5, 0.0)),
+                       ("zgbsvx,equil=false", ("zgbsvx", False, False, 1, -1, 5, 0.0)),
+                       ("zgbsvx,equil=true", ("zgbsvx", True, False, 1, -1, 5, 0.0)),
+                       ("zcgbsvx,reuse=false,aiter=1,siter=-1,diter=5,tolsc=0", ("zcgbsvx", False, False, 1, -1, 5, 0.0)),
+                       ("zcgbsvx,reuse=true,aiter=1,siter=-1,diter=5,tolsc=0", ("zcgbsvx", False, True, 1, -1, 5, 0.0)),
+                       ("ZCGBSVX, reuse=TRUE, aiter=5, siter=25, diter=5, tolsc=0", ("zcgbsvx", False, True, 5, 25, 5, 0.0)),
+                       ("", ("zcgbsvx", False, False, 1, -1, 5, 0.0))):
+        s = sz.SolverSpec.parse(text)
+        assert (s.method, s.equil, s.reuse, s.aiter, s.siter, s.diter, s.tolsc) == want, text
+        cs = s.c()
+        assert (cs.method, cs.equil, cs.reuse, cs.siter) == ({"zgbsv": 0, "zcgbsvx": 1, "zgbsvx": 2}[want[0]],
+                                                             int(want[1]), int(want[2]), want[4])
+    assert sz.SolverSpec.parse("zgbsv").in_place() and not sz.SolverSpec.parse("zgbsvx").in_place()
+    for bad in ("zgbsv,equil=true", "zgbsvx,reuse=true", "zcgbsvx,equil=true", "zcgbsvx,aiter", "zcgbsvx,aiter=1,aiter=2",
+                "dgbsv", "zgbsvx,", "zcgbsvx,reuse=maybe"):
         with pytest.raises(ValueError):
             sz.SolverSpec.parse(bad)
 
