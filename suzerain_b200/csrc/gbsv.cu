@@ -651,11 +651,14 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     }
     // zcgbsvx with its default eps tolerance: refinement around the fused kernel (the factors
     // are recomputed per step instead of being stored); SZB_INVERT=v1 keeps the generic kernel
-    if (spec->method == SZB_SOLVER_ZCGBSVX && nextra == 0 && spec->tolsc == 0.0 && spec->aiter >= 1) {
+    // Likewise zgbsvx without equilibration: zgbtrs + zgbrfs around the fused kernel.
+    const bool refined_zc = spec->method == SZB_SOLVER_ZCGBSVX && spec->tolsc == 0.0 && spec->aiter >= 1;
+    const bool refined_zx = spec->method == SZB_SOLVER_ZGBSVX && !spec->equil;
+    if (nextra == 0 && (refined_zc || refined_zx)) {
         static const bool generic = [] { const char *e = std::getenv("SZB_INVERT"); return e && e[0] == 'v' && e[1] == '1'; }();
         if (!generic) {
-            const int rc = invert_refined_dispatch(op, spec->aiter, spec->diter, phi, npencil, d_km, d_kn, d_index,
-                                                   reinterpret_cast<cplx *>(d_state), field_stride, pencil_stride,
+            const int rc = invert_refined_dispatch(op, refined_zx ? 1 : 0, spec->aiter, spec->diter, phi, npencil, d_km, d_kn,
+                                                   d_index, reinterpret_cast<cplx *>(d_state), field_stride, pencil_stride,
                                                    d_ipiv, d_info, d_iters, (cudaStream_t) stream);
             if (rc <= 0) return rc;
         }

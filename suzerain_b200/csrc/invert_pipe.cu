@@ -941,6 +941,7 @@ struct ResidualArgs {
     const cplx *b;                  // [npencil][5][n] right hand sides (wall rows still to be zeroed)
     cplx *r;                        // [npencil][5][n] in: correction d (if add), out: residual
     int add, it, aiter, dmax;
+    int mode;                       // 0: zcgbsvx (2-norm, stagnation), 1: zgbrfs (componentwise backward error)
     double tol;
     double *res, *lastres; int *diter, *cont;
 };
@@ -964,6 +965,7 @@ residual_kernel(const ResidualArgs A)
     cplx *stage = q; q += P * CW;
     cplx *xs = q; q += N;
     cplx *rs = q; q += N;
+    double *ra = reinterpret_cast<double *>(q); q += (N + 1) / 2;      // zgbrfs: |b| + |A^T| |x|
     S.tref = reinterpret_cast<unsigned char *>(q);
     S.tblk = S.tref + MAXTERMS;
     for (int t = tid; t < MAXTERMS; t += 256) S.tref[t] = K.terms->ref[t];
@@ -986,6 +988,7 @@ residual_kernel(const ResidualArgs A)
             if (K.with_bc && f < 4 && ((y == 0 && K.wall_begin == 0) || (y == n - 1 && K.wall_end == 2)))
                 bv = cplx(0.0, 0.0);
             rs[5 * y + f] = bv;
+            ra[5 * y + f] = cabs1(bv);
         }
         __syncthreads();
         for (int y = 0; y <= K.ku; ++y) compute_coef<W>(K, S, y, tid, 256);
@@ -1002,39 +1005,61 @@ residual_kernel(const ResidualArgs A)
                     const int I = 5 * yI + sI, J0 = I - KL;
                     int ci = (tid - J0) % CW; if (ci < 0) ci += CW;
                     const int J = J0 + ci;
-                    if (ci <= W::KV && J >= 0 && J < N) submul(rs[J], stage[sI * CW + tid], xs[I]);
+                    if (ci <= W::KV && J >= 0 && J < N) {
+                        const cplx a = stage[sI * CW + tid], xv = xs[I];
+                        submul(rs[J], a, xv);
+                        if (A.mode) ra[J] += cabs1(a) * cabs1(xv);
+                    }
                 }
             }
             __syncthreads();
         }
         double s2 = 0.0;
+        // zgbrfs.f: safe1 = nz safmin, safe2 = safe1 / eps guard tiny denominators
+        const double safe1 = min(W::KL + W::KU + 2, N + 1) * 2.2250738585072014e-308, safe2 = safe1 / 1.1102230246251565e-16;
         for (int k = tid; k < N; k += 256) {
             const int f = k / n, y = k - f * n;
             const cplx v = rs[5 * y + f];
             r[k] = v;
-            s2 += v.x * v.x + v.y * v.y;
+            if (A.mode) {
+                const double den = ra[5 * y + f], num = cabs1(v);
+                s2 = fmax(s2, den > safe2 ? num / den : (num + safe1) / (den + safe1));
+            } else s2 += v.x * v.x + v.y * v.y;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, s2, o);
+            s2 = A.mode ? fmax(s2, other) : s2 + other;
+        }
         if ((tid & 31) == 0) s_red[tid >> 5] = s2;
         __syncthreads();
         if (tid == 0) {
             double t = 0.0;
-            for (int w = 0; w < 8; ++w) t += s_red[w];
-            const double res = sqrt(t);
-            // dsgbsvx.def:271-284: stagnation once diter >= aiter, else keep the residual
-            const bool stop = A.it >= A.aiter && A.lastres[p] < 2.0 * res;
-            A.diter[p] = A.it;
-            A.res[p] = res;
-            if (!stop) A.lastres[p] = res;
-            A.cont[p] = !stop && A.it < A.dmax && res > A.tol;
+            for (int w = 0; w < 8; ++w) t = A.mode ? fmax(t, s_red[w]) : t + s_red[w];
+            if (A.mode) {
+                // zgbrfs.f: go on while berr > eps, berr at least halved, at most ITMAX = 5 corrections
+                const double berr = t;
+                const bool go = berr > 1.1102230246251565e-16 && 2.0 * berr <= A.lastres[p] && A.it < 5;
+                A.diter[p] = A.it;
+                A.res[p] = berr;
+                if (go) A.lastres[p] = berr;
+                A.cont[p] = go;
+            } else {
+                const double res = sqrt(t);
+                // dsgbsvx.def:271-284: stagnation once diter >= aiter, else keep the residual
+                const bool stop = A.it >= A.aiter && A.lastres[p] < 2.0 * res;
+                A.diter[p] = A.it;
+                A.res[p] = res;
+                if (!stop) A.lastres[p] = res;
+                A.cont[p] = !stop && A.it < A.dmax && res > A.tol;
+            }
         }
         __syncthreads();
     }
 }
 
 __global__ void refine_gather_kernel(int npencil, int N, int n, const int *index, const cplx *state,
-                                     size_t fs, size_t ps, cplx *b, double *lastres)
+                                     size_t fs, size_t ps, cplx *b, double *lastres, double lastres0)
 {
     const int p = blockIdx.x;
     const cplx *v = state + (index ? (size_t) index[p] : (size_t) p) * ps;
@@ -1046,7 +1071,7 @@ __global__ void refine_gather_kernel(int npencil, int N, int n, const int *index
         s2 += val.x * val.x + val.y * val.y;
     }
     (void) s2; (void) npencil;
-    if (threadIdx.x == 0) lastres[p] = 0.0;
+    if (threadIdx.x == 0) lastres[p] = lastres0;
 }
 
 __global__ void refine_compact_kernel(int npencil, const int *cont, const int *info, const double *km,
@@ -1067,8 +1092,8 @@ __global__ void refine_finish_kernel(int npencil, const int *info, const int *di
 template <class W>
 int launch_residual(const szb_imexop *op, ResidualArgs &A, cudaStream_t stream)
 {
-    const size_t smem = sizeof(cplx) * ((size_t) W::CR * W::NCOEF + MAXTERMS + P * W::CW + 2 * (size_t) op->A.N)
-                        + MAXTERMS + 96;
+    const size_t smem = sizeof(cplx) * ((size_t) W::CR * W::NCOEF + MAXTERMS + P * W::CW + 2 * (size_t) op->A.N
+                                       + ((size_t) op->A.N + 1) / 2) + MAXTERMS + 96;
     if (smem > 200 * 1024) return 1;
     static size_t configured = 0;
     if (smem > configured) {
@@ -1121,10 +1146,10 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
 }
 
 
-// zcgbsvx with the default eps tolerance (tolsc == 0, no single-precision attempt) on top of the
-// fused kernel.  Returns 0 when done, 1 when not applicable (the caller then uses the generic
+// zcgbsvx with the default eps tolerance (tolsc == 0, no single-precision attempt; mode 0) or
+// zgbsvx without equilibration (zgbtrs + zgbrfs refinement; mode 1) on top of the fused kernel.  Returns 0 when done, 1 when not applicable (the caller then uses the generic
 // kernel), < 0 on error.  Synchronises the stream once per refinement step (active-list count).
-int invert_refined_dispatch(const szb_imexop *op, int aiter, int dmax, const double phi[2], int npencil,
+int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                             int *d_iters, cudaStream_t stream)
@@ -1155,7 +1180,9 @@ int invert_refined_dispatch(const szb_imexop *op, int aiter, int dmax, const dou
     int *info2 = reinterpret_cast<int *>(w); w += ni;
     int *count = reinterpret_cast<int *>(w);
 
-    refine_gather_kernel<<<npencil, 128, 0, stream>>>(npencil, N, n, d_index, d_state, fs, ps, B, lastres);
+    if (mode) { aiter = 1; dmax = 5; }                    // zgbrfs: ITMAX
+    refine_gather_kernel<<<npencil, 128, 0, stream>>>(npencil, N, n, d_index, d_state, fs, ps, B, lastres,
+                                                      mode ? 3.0 : 0.0);
     count_launch();
     // first pass: x = 0 + (LU)^-T b, in place in the state
     int rc = invert_pipe_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info,
@@ -1165,7 +1192,7 @@ int invert_refined_dispatch(const szb_imexop *op, int aiter, int dmax, const dou
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
     A.nlist = npencil; A.pos = nullptr; A.index = d_index;
     A.x = d_state; A.fs = fs; A.ps = ps; A.b = B; A.r = R;
-    A.add = 0; A.it = 0; A.aiter = aiter; A.dmax = dmax;
+    A.add = 0; A.it = 0; A.aiter = aiter; A.dmax = dmax; A.mode = mode;
     A.tol = 2.220446049250313e-16 * 0.5;                  // dlamch('E')
     A.res = res; A.lastres = lastres; A.diter = diter; A.cont = cont;
     // the reference starts from lastres = 3 (|b| + 1): never a stagnation at it = 0 unless aiter = 0;

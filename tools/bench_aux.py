@@ -50,4 +50,25 @@ ms = timed(lambda: [sz.diffwave_apply(1, 1, 1.0, a, g) for a in xs])
 # apply reads and writes kept pencils, only writes dealiased ones
 out["kernels"]["diffwave_apply"] = {"ms": ms, "GB/s": 2 * nbytes / ms / 1e6, "frac": 2 * nbytes / ms / 1e6 / peak,
                                     "note": "upper bound on bytes: dealiased pencils are written, not read"}
+
+# invert under the other linearisation / solver specifications, all active pencils
+act = np.flatnonzero(wl.act)
+km = torch.from_numpy(wl.km[act]).to(dev); kn = torch.from_numpy(wl.kn[act]).to(dev)
+st0 = torch.from_numpy(wl.host_state()[act]).to(dev)
+info = torch.zeros(len(act), dtype=torch.int32, device=dev)
+phi = wl.phis(0)[2]
+out["invert"] = {"pencils": int(len(act)), "note": "ms per call over all active pencils, state resident"}
+for lin, text, reps in (("rhome_xyz", "zgbsv", 5), ("rhome_xyz", "zcgbsvx", 3), ("rhome_xyz", "zgbsvx,equil=false", 2),
+                        ("rhome_xyz", "zgbsvx,equil=true", 2), ("rhome_y", "zgbsv", 10), ("rhome_y", "zcgbsvx", 3)):
+    op = wl.make_imexop().set_linearization(lin)
+    spec = sz.SolverSpec.parse(text)
+    st = st0.clone()
+
+    def run():
+        st.copy_(st0)
+        op.invert_batch(spec, phi, km, kn, st, info=info)
+    ms_copy = timed(lambda: st.copy_(st0), reps=10)
+    ms = timed(run, reps=reps) - ms_copy
+    assert int(info.max()) == 0
+    out["invert"][f"{lin} {text}"] = {"ms": ms}
 print(json.dumps(out))
