@@ -251,6 +251,33 @@ def base_line(args, wl):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run on (and first-touch pinned host memory from) the cores of the NUMA
+    node the GPU hangs off, so that the host<->device copies of the e2e leg do not cross the
+    socket interconnect.  Best effort; returns a description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += range(int(lo), int(hi or lo) + 1)
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return f"numa node {node}: no allowed cpus"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception as e:                                   # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -263,6 +290,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    binding = bind_to_gpu_numa_node(local) if world > 1 else "single process"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -359,7 +387,8 @@ def run_b200(args):
         e2e = {"value": e2e_s * 1e9 / (wl.gridpoints * world), "unit": "ns/gridpoint/substep",
                "h2d_bytes_per_step": 3 * state_bytes, "d2h_bytes_per_step": 2 * state_bytes,
                "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-               "api": "szb_operator_{accumulate,invert}_mass_plus_scaled_operator on pinned host state"}
+               "api": "szb_operator_{accumulate,invert}_mass_plus_scaled_operator on pinned host state",
+               "host_binding": binding}
 
     if rank != 0:
         if world > 1:

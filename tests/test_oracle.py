@@ -358,3 +358,29 @@ def test_reference_diffwave_matches_formula():
         assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
         got = oref.diffwave(dx, dz, alpha, x, Lx, Lz, grid, beta=beta, y=y)
         assert np.abs(got - (want + beta * y)).max() <= 1e-13 * np.abs(want + beta * y).max()
+
+
+def test_reference_solver_specifications_agree_like_its_own_test():
+    """apps/perfect/test_implicit_solvers.sh:24-50 on the tiny synthetic case: the six --solver
+    specifications, run through the reference's own zgbsvx / zcgbsvx with its solver-state chain
+    (oracle/_ref, ref_invert_spec_batch), agree with plain zgbsv."""
+    pytest.importorskip("scipy")
+    import parity_common as pc
+    case = pc.make_case("tiny_16x24x16")
+    try:
+        P = pc.oracle_problem(case, "ref")
+    except Exception as e:                                   # noqa: BLE001
+        pytest.skip(f"oracle/_ref not built: {e}")
+    npen = len(case.km)
+    x = case.x.reshape(npen, -1)
+    base = P.invert("zgbsv", case.phi, case.km, case.kn, x)["x"]
+    for kw in (dict(method="zgbsv"), dict(method="zgbsvx", equil=False), dict(method="zgbsvx", equil=True),
+               dict(method="zcgbsvx"), dict(method="zcgbsvx", reuse=True, rowlen=8),
+               dict(method="zcgbsvx", reuse=True, aiter=5, siter=25, rowlen=8)):
+        r = P.invert_spec(case.phi, case.km, case.kn, x, **kw)
+        assert r["info"] == 0, kw
+        assert pc.relmax(r["x"], base) <= 1e-13, kw
+    # larger |phi| makes zlaqgb equilibrate: rows at 100x, rows and columns at 1000x
+    for scale, code in ((100, 1), (1000, 3)):
+        r = P.invert_spec(case.phi * scale, case.km, case.kn, x, method="zgbsvx", equil=True)
+        assert r["info"] == 0 and set(r["stats"][:, 0].astype(int)) == {code}
