@@ -606,14 +606,18 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
     if (npencil == 0) return 0;
 
     // linearize::rhome_y (operator_hybrid_isothermal.cpp:691-761): the operator does not depend on
-    // the wavenumbers.  zgbsv without extra right hand sides: one factorisation, one pair of
-    // triangular sweeps per pencil (rhome_y.cu); otherwise the general kernels at km = kn = 0.
+    // the wavenumbers: one factorisation, one pair of triangular sweeps per right hand side, and
+    // refinement around it for zcgbsvx / zgbsvx (rhome_y.cu); anything else (equilibration, scaled
+    // tolerances) runs the general kernels at km = kn = 0.
     if (op->linearization == SZB_LINEARIZE_RHOME_Y) {
-        if (spec->method == SZB_SOLVER_ZGBSV && nextra == 0) {
-            int rc = invert00_dispatch(op, phi, npencil, d_index, reinterpret_cast<cplx *>(d_state), field_stride,
-                                       pencil_stride, d_ipiv, d_info, (cudaStream_t) stream);
-            if (rc == 0 && d_iters) SZB_CUDA_OK(cudaMemsetAsync(d_iters, 0, sizeof(int) * (size_t) npencil, (cudaStream_t) stream));
-            return rc;
+        const int mode = spec->method == SZB_SOLVER_ZGBSV ? -1
+                       : (spec->method == SZB_SOLVER_ZCGBSVX && spec->tolsc == 0.0) ? 0
+                       : (spec->method == SZB_SOLVER_ZGBSVX && !spec->equil) ? 1 : -2;
+        if (mode >= -1) {
+            const int rc = invert00_dispatch(op, mode, spec->aiter, spec->diter, phi, npencil, d_index,
+                                             reinterpret_cast<cplx *>(d_state), field_stride, pencil_stride, nextra,
+                                             reinterpret_cast<cplx *>(d_extra), d_ipiv, d_info, d_iters, (cudaStream_t) stream);
+            if (rc <= 0) return rc;
         }
         if ((size_t) npencil > op->zero_count) {
             if (op->d_zero) SZB_CUDA_OK(cudaFree(op->d_zero));

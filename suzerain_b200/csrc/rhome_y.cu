@@ -610,16 +610,197 @@ solve00_tpp_kernel(const Solve00Args A)
     for (int y = YB - 1; y >= 0; --y) release(y);
 }
 
-}  // namespace
+// ---------------------------------------------------------------------------
+// Refinement around the shared factorisation (zcgbsvx with the eps tolerance, dsgbsvx.def:131-318;
+// zgbsvx without equilibration, zgbrfs.f): r = b - A^T x with the UNFACTORED operator, one thread
+// per pencil, same ring of collocation points as the sweeps; the five columns of P A^T P^T that
+// belong to step b are staged by the CTA (zero padded so that no band test is needed).  Norms and
+// stopping rules are thread-local.
+// ---------------------------------------------------------------------------
+__global__ void extract_papt_kernel(int N, int kl, int ku, const cplx *lu, int ldlu, cplx *papt)
+{
+    const int ld = kl + 1 + ku, total = N * ld;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int j = e / ld, r = e - j * ld, i = j - ku + r;
+        papt[e] = (i >= 0 && i < N) ? lu[(size_t) j * ldlu + kl + r] : cplx(0.0, 0.0);
+    }
+}
 
-// Returns 0 when done, < 0 on error.
-int invert00_dispatch(const szb_imexop *op, const double phi[2], int npencil, const int *d_index,
-                      cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info, cudaStream_t stream)
+struct Residual00Args {
+    int N, n, npencil;
+    const cplx *papt;               // [N][LD], zero outside the matrix
+    const int *index; cplx *x; size_t fs, ps;       // solution (state layout)
+    const cplx *b;                  // [npencil][5][n] right hand sides (wall rows still to be zeroed)
+    cplx *r;                        // [npencil][5][n] in: correction d (if add), out: residual
+    int with_bc, wall_begin, wall_end;
+    int add, it, aiter, dmax, mode;
+    double tol;
+    double *res, *lastres; int *diter, *cont, *count;
+};
+
+template <int KL>
+struct Res00 {
+    static constexpr int KU = KL, LD = KL + 1 + KU, PADL = 5, LDP = LD + 10;
+    static constexpr int YB = (KL + 4) / 5;            // points either side of b that column block b touches
+    static constexpr int XRY = 2 * YB + 3, XR = 5 * XRY;
+    static constexpr int TS = 5 * LDP;
+    static constexpr int NW = (sizeof(cplx) * (4 * 32 * XR + 2 * TS) + 1024 <= 227 * 1024) ? 4 : 3;
+    static constexpr size_t smem = sizeof(cplx) * ((size_t) NW * 32 * XR + 2 * TS);
+    static_assert(5 * YB <= KU + 1, "padding covers the rows of the outermost points");
+};
+
+template <int KL>
+__global__ void __launch_bounds__(32 * Res00<KL>::NW)
+residual00_kernel(const Residual00Args A)
+{
+    using T = Res00<KL>;
+    constexpr int KU = T::KU, LD = T::LD, PADL = T::PADL, LDP = T::LDP, YB = T::YB, XRY = T::XRY, TS = T::TS, NT = 32 * T::NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = A.n, N = A.N;
+    const int p = blockIdx.x * NT + tid;
+    const bool inrange = p < A.npencil;
+    // pencils that stopped earlier sit this pass out
+    const bool active = inrange && (A.it == 0 || A.cont[p]);
+    cplx *tab = reinterpret_cast<cplx *>(smem_raw);                               // [2][5][LDP]
+    cplx *ring = tab + 2 * TS + (size_t) warp * 32 * T::XR + lane;
+    const size_t pp = active ? (size_t) p : 0;
+    cplx *xg = A.x + (A.index ? (size_t) A.index[pp] : pp) * A.ps;
+    const cplx *bg = A.b + pp * N;
+    cplx *rg = A.r + pp * N;
+    const size_t fs = A.fs;
+    const bool bc_lo = A.with_bc && A.wall_begin == 0, bc_hi = A.with_bc && A.wall_end == 2;
+    for (int e = tid; e < 2 * TS; e += NT) tab[e] = cplx(0.0, 0.0);
+    __syncthreads();
+
+    auto slot = [&](int y) { return ring + (size_t) ((y + XRY) % XRY) * 5 * 32; };
+    // x (+ d) of collocation point y into registers; written back to the state when corrected
+    auto fetch = [&](int y, cplx (&v)[5]) {
+#pragma unroll
+        for (int f = 0; f < 5; ++f) v[f] = cplx(0.0, 0.0);
+        if (active && y >= 0 && y < n) {
+#pragma unroll
+            for (int f = 0; f < 5; ++f) v[f] = xg[(size_t) f * fs + y];
+            if (A.add) {
+#pragma unroll
+                for (int f = 0; f < 5; ++f) { v[f] += rg[(size_t) f * n + y]; xg[(size_t) f * fs + y] = v[f]; }
+            }
+        }
+    };
+    auto put = [&](int y, const cplx (&v)[5]) {
+        cplx *d = slot(y);
+#pragma unroll
+        for (int f = 0; f < 5; ++f) d[f * 32] = v[f];
+    };
+    auto request_tab = [&](int b) {
+        if (b < n) {
+            cplx *d = tab + (b & 1) * TS;
+            const cplx *src = A.papt + (size_t) 5 * b * LD;
+            for (int e = tid; e < 5 * LD; e += NT) {
+                const int m = e / LD, rr = e - m * LD;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                             :: "r"((unsigned) __cvta_generic_to_shared(d + m * LDP + PADL + rr)), "l"(src + e) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    cplx nx[5];
+    for (int y = -YB; y <= YB; ++y) { fetch(y, nx); put(y, nx); }
+    fetch(YB + 1, nx);
+    request_tab(0);
+    double s2 = 0.0;
+    const double safe1 = min(KL + KU + 2, N + 1) * 2.2250738585072014e-308, safe2 = safe1 / 1.1102230246251565e-16;
+    for (int b = 0; b < n; ++b) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                            // block b staged; every warp is done with block b - 1
+        request_tab(b + 1);
+        if (b > 0) { put(b + YB, nx); fetch(b + YB + 1, nx); }
+        const cplx *tb = tab + (b & 1) * TS;
+        cplx acc[5]; double ra[5];
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            cplx bv(0.0, 0.0);
+            if (active) bv = bg[(size_t) m * n + b];
+            if (m < 4 && ((b == 0 && bc_lo) || (b == n - 1 && bc_hi))) bv = cplx(0.0, 0.0);
+            acc[m] = bv; ra[m] = cabs1(bv);
+        }
+        for (int dy = -YB; dy <= YB; ++dy) {
+            const cplx *xr = slot(b + dy);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+                const cplx xv = xr[f * 32];
+                const int base = PADL + KU + 5 * dy + f;            // + m * LDP - m
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    const cplx a = tb[m * LDP + base - m];
+                    submul(acc[m], a, xv);
+                    if (A.mode) ra[m] += cabs1(a) * cabs1(xv);
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                rg[(size_t) m * n + b] = acc[m];
+                if (A.mode) {
+                    const double num = cabs1(acc[m]);
+                    s2 = fmax(s2, ra[m] > safe2 ? num / ra[m] : (num + safe1) / (ra[m] + safe1));
+                } else s2 += acc[m].x * acc[m].x + acc[m].y * acc[m].y;
+            }
+        }
+    }
+    bool go = false;
+    if (active) {
+        if (A.mode) {
+            const double berr = s2;
+            go = berr > 1.1102230246251565e-16 && 2.0 * berr <= A.lastres[p] && A.it < 5;
+            A.diter[p] = A.it; A.res[p] = berr;
+            if (go) A.lastres[p] = berr;
+        } else {
+            const double res = sqrt(s2);
+            const bool stop = A.it >= A.aiter && A.lastres[p] < 2.0 * res;
+            A.diter[p] = A.it; A.res[p] = res;
+            if (!stop) A.lastres[p] = res;
+            go = !stop && A.it < A.dmax && res > A.tol;
+        }
+        A.cont[p] = go;
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, go);
+    if (lane == 0 && any) atomicAdd(A.count, __popc(any));
+}
+
+__global__ void gather00_kernel(int npencil, int N, int n, const int *index, const cplx *state, size_t fs, size_t ps,
+                                cplx *b, double *lastres, double lastres0)
+{
+    const int p = blockIdx.x;
+    const cplx *v = state + (index ? (size_t) index[p] : (size_t) p) * ps;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const int f = k / n, y = k - f * n;
+        b[(size_t) p * N + k] = v[(size_t) f * fs + y];
+    }
+    if (threadIdx.x == 0) lastres[p] = lastres0;
+}
+
+__global__ void finish00_kernel(int npencil, const int *info, const int *diter, int *iters)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npencil && iters) iters[p] = info[p] ? -1 : diter[p];
+}
+
+// The factorisation of the km = kn = 0 operator and everything derived from it, in op->d_work00.
+struct Ctx00 {
+    int N, n, KL, KU, ldab, kv, nblk;
+    bool tpp;
+    cplx *LU, *fw_tri, *fw_upd, *bw_tri, *bw_upd, *papt;
+    int *ipiv, *info1; double *zero; unsigned char *plain;
+};
+
+int prepare00(const szb_imexop *op, const double phi[2], bool want_papt, Ctx00 &C, cudaStream_t stream)
 {
     const int N = op->A.N, KL = op->A.KL, KU = op->A.KU, ldab = op->A.LD + KL, kv = KL + KU;
     if (kv + 3 > FWR || KL > BWR || kv >= 128 || KL * kv > FACTOR00_TASKS * 512) return -1;
     const int nblk = (N + 3) / 4;
-    // workspace: LU | regrouped factors | ipiv | info | zero wavenumbers | plain flags
+    // workspace: LU | regrouped factors | ipiv | info | zero wavenumbers | plain flags | unfactored operator
     const size_t b_lu = sizeof(cplx) * (size_t) ldab * N;
     // (sized for either grouping: blocks of four columns, or of five = one collocation point)
     const size_t n5 = (size_t) op->n;
@@ -629,7 +810,8 @@ int invert00_dispatch(const szb_imexop *op, const double phi[2], int npencil, co
     const size_t b_bu = sizeof(cplx) * std::max((size_t) nblk * 4 * BWR, n5 * 5 * KL);
     const size_t b_ip = ((sizeof(int) * (size_t) N) + 15) & ~(size_t) 15;
     const size_t b_pl = ((size_t) std::max(nblk, op->n) + 15) & ~(size_t) 15;
-    const size_t need = b_lu + b_ft + b_fu + b_bt + b_bu + b_ip + 16 + 16 + b_pl;
+    const size_t b_pa = sizeof(cplx) * (size_t) op->A.LD * N;
+    const size_t need = b_lu + b_ft + b_fu + b_bt + b_bu + b_ip + 16 + 16 + b_pl + b_pa;
     if (need > op->work00_bytes) {
         if (op->d_work00) SZB_CUDA_OK(cudaFree(op->d_work00));
         op->d_work00 = nullptr; op->work00_bytes = 0;
@@ -637,68 +819,175 @@ int invert00_dispatch(const szb_imexop *op, const double phi[2], int npencil, co
         op->work00_bytes = need;
     }
     unsigned char *w = static_cast<unsigned char *>(op->d_work00);
-    cplx *LU = reinterpret_cast<cplx *>(w); w += b_lu;
-    cplx *fw_tri = reinterpret_cast<cplx *>(w); w += b_ft;
-    cplx *fw_upd = reinterpret_cast<cplx *>(w); w += b_fu;
-    cplx *bw_tri = reinterpret_cast<cplx *>(w); w += b_bt;
-    cplx *bw_upd = reinterpret_cast<cplx *>(w); w += b_bu;
-    int *ipiv = reinterpret_cast<int *>(w); w += b_ip;
-    int *info1 = reinterpret_cast<int *>(w); w += 16;
-    double *zero = reinterpret_cast<double *>(w); w += 16;
-    unsigned char *plain = w;
-    SZB_CUDA_OK(cudaMemsetAsync(zero, 0, 16, stream));
-    int rc = szb_imexop_pack_batch(op, phi, 1, zero, zero + 1, 1, 1, reinterpret_cast<szb_complex *>(LU), stream);
+    C.N = N; C.n = op->n; C.KL = KL; C.KU = KU; C.ldab = ldab; C.kv = kv; C.nblk = nblk;
+    C.LU = reinterpret_cast<cplx *>(w); w += b_lu;
+    C.fw_tri = reinterpret_cast<cplx *>(w); w += b_ft;
+    C.fw_upd = reinterpret_cast<cplx *>(w); w += b_fu;
+    C.bw_tri = reinterpret_cast<cplx *>(w); w += b_bt;
+    C.bw_upd = reinterpret_cast<cplx *>(w); w += b_bu;
+    C.ipiv = reinterpret_cast<int *>(w); w += b_ip;
+    C.info1 = reinterpret_cast<int *>(w); w += 16;
+    C.zero = reinterpret_cast<double *>(w); w += 16;
+    C.plain = w; w += b_pl;
+    C.papt = reinterpret_cast<cplx *>(w);
+    SZB_CUDA_OK(cudaMemsetAsync(C.zero, 0, 16, stream));
+    int rc = szb_imexop_pack_batch(op, phi, 1, C.zero, C.zero + 1, 1, 1, reinterpret_cast<szb_complex *>(C.LU), stream);
     if (rc) return rc;
-    {
-        const size_t fsm = sizeof(cplx) * (size_t) (kv + 1 + FACTOR00_AHEAD) * ldab;
-        if (fsm > 48 * 1024)
-            SZB_CUDA_OK(cudaFuncSetAttribute(factor00_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsm));
-        factor00_kernel<<<1, 512, fsm, stream>>>(N, KL, KU, LU, ldab, ipiv, info1);
+    if (want_papt) {
+        extract_papt_kernel<<<op->sm_count, 256, 0, stream>>>(N, KL, KU, C.LU, ldab, C.papt);
         count_launch();
     }
-    Solve00Args A;
-    A.N = N; A.n = op->n; A.kl = KL; A.ku = KU; A.ldab = ldab; A.nblk = nblk;
-    A.ab = LU; A.fw_tri = fw_tri; A.fw_upd = fw_upd; A.bw_tri = bw_tri; A.bw_upd = bw_upd; A.plain = plain;
-    A.ipiv = ipiv; A.info1 = info1;
-    A.npencil = npencil; A.index = d_index; A.state = d_state; A.fs = fs; A.ps = ps;
-    A.with_bc = 1; A.wall_begin = op->iso.enforce_lower ? 0 : 1; A.wall_end = op->iso.enforce_upper ? 2 : 1;
-    A.ipiv_out = d_ipiv; A.info_out = d_info;
+    const size_t fsm = sizeof(cplx) * (size_t) (kv + 1 + FACTOR00_AHEAD) * ldab;
+    if (fsm > 48 * 1024)
+        SZB_CUDA_OK(cudaFuncSetAttribute(factor00_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsm));
+    factor00_kernel<<<1, 512, fsm, stream>>>(N, KL, KU, C.LU, ldab, C.ipiv, C.info1);
+    count_launch();
     static const bool use_warp = std::getenv("SZB_RHOME_Y_WARP") != nullptr;
-    const bool tpp = !use_warp && N == 5 * op->n && KL == KU && (KL == 14 || KL == 24 || KL == 34 || KL == 44);
-    if (tpp) {
-        // thread per pencil, blocks of five rows
-        A.nblk = op->n;
-        regroup5_kernel<<<op->sm_count, 256, 0, stream>>>(N, KL, KU, LU, ldab, ipiv, op->n, fw_tri, fw_upd, bw_tri, bw_upd, plain);
-        count_launch();
+    C.tpp = !use_warp && N == 5 * op->n && KL == KU && (KL == 14 || KL == 24 || KL == 34 || KL == 44);
+    if (C.tpp)
+        regroup5_kernel<<<op->sm_count, 256, 0, stream>>>(N, KL, KU, C.LU, ldab, C.ipiv, op->n, C.fw_tri, C.fw_upd,
+                                                         C.bw_tri, C.bw_upd, C.plain);
+    else
+        regroup00_kernel<<<op->sm_count, 256, 0, stream>>>(N, KL, KU, C.LU, ldab, C.ipiv, nblk, C.fw_tri, C.fw_upd,
+                                                          C.bw_tri, C.bw_upd, C.plain);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// state <- (LU)^-T P state for npencil right hand sides against the prepared factorisation
+int solve00(const szb_imexop *op, const Ctx00 &C, int npencil, const int *d_index, cplx *d_state, size_t fs, size_t ps,
+            int with_bc, int *d_ipiv, int *d_info, cudaStream_t stream)
+{
+    Solve00Args A;
+    A.N = C.N; A.n = C.n; A.kl = C.KL; A.ku = C.KU; A.ldab = C.ldab; A.nblk = C.tpp ? C.n : C.nblk;
+    A.ab = C.LU; A.fw_tri = C.fw_tri; A.fw_upd = C.fw_upd; A.bw_tri = C.bw_tri; A.bw_upd = C.bw_upd; A.plain = C.plain;
+    A.ipiv = C.ipiv; A.info1 = C.info1;
+    A.npencil = npencil; A.index = d_index; A.state = d_state; A.fs = fs; A.ps = ps;
+    A.with_bc = with_bc; A.wall_begin = op->iso.enforce_lower ? 0 : 1; A.wall_end = op->iso.enforce_upper ? 2 : 1;
+    A.ipiv_out = d_ipiv; A.info_out = d_info;
+    int rc = 0;
+    if (C.tpp) {
         auto go = [&](auto kern, size_t smem, int nt) -> int {
             if (smem > 48 * 1024)
                 SZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             kern<<<(npencil + nt - 1) / nt, nt, smem, stream>>>(A);
             return 0;
         };
-        rc = KL == 14 ? go(solve00_tpp_kernel<28, 14>, Tpp<28, 14>::smem, 32 * Tpp<28, 14>::NW)
-           : KL == 24 ? go(solve00_tpp_kernel<48, 24>, Tpp<48, 24>::smem, 32 * Tpp<48, 24>::NW)
-           : KL == 34 ? go(solve00_tpp_kernel<68, 34>, Tpp<68, 34>::smem, 32 * Tpp<68, 34>::NW)
-                      : go(solve00_tpp_kernel<88, 44>, Tpp<88, 44>::smem, 32 * Tpp<88, 44>::NW);
-        if (rc) return rc;
+        rc = C.KL == 14 ? go(solve00_tpp_kernel<28, 14>, Tpp<28, 14>::smem, 32 * Tpp<28, 14>::NW)
+           : C.KL == 24 ? go(solve00_tpp_kernel<48, 24>, Tpp<48, 24>::smem, 32 * Tpp<48, 24>::NW)
+           : C.KL == 34 ? go(solve00_tpp_kernel<68, 34>, Tpp<68, 34>::smem, 32 * Tpp<68, 34>::NW)
+                        : go(solve00_tpp_kernel<88, 44>, Tpp<88, 44>::smem, 32 * Tpp<88, 44>::NW);
     } else {
-    regroup00_kernel<<<op->sm_count, 256, 0, stream>>>(N, KL, KU, LU, ldab, ipiv, nblk, fw_tri, fw_upd, bw_tri, bw_upd, plain);
+        const int nw = SOLVE00_WARPS;
+        const size_t smem = sizeof(cplx) * (size_t) nw * (4 * C.nblk + FWR + 4);
+        const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(4, (224 * 1024) / (smem + 1024)));
+        const int grid = std::min((npencil + nw - 1) / nw, per_sm * op->sm_count);
+        const int fwp = (C.kv + 3 + 31) / 32, bwp = (C.KL + 31) / 32;
+        auto go = [&](auto kern) -> int {
+            if (smem > 48 * 1024)
+                SZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            kern<<<grid, 32 * nw, smem, stream>>>(A);
+            return 0;
+        };
+        rc = fwp == 1 ? go(solve00_kernel<1, 1>) : fwp == 2 ? go(solve00_kernel<2, 1>)
+           : bwp == 1 ? go(solve00_kernel<3, 1>) : go(solve00_kernel<3, 2>);
+    }
+    if (rc) return rc;
     count_launch();
-    const int nw = SOLVE00_WARPS;
-    const size_t smem = sizeof(cplx) * (size_t) nw * (4 * nblk + FWR + 4);
-    const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(4, (224 * 1024) / (smem + 1024)));
-    const int grid = std::min((npencil + nw - 1) / nw, per_sm * op->sm_count);
-    const int fwp = (kv + 3 + 31) / 32, bwp = (KL + 31) / 32;
-    auto go = [&](auto kern) -> int {
-        if (smem > 48 * 1024)
-            SZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        kern<<<grid, 32 * nw, smem, stream>>>(A);
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// linearize::rhome_y invert.  mode < 0: zgbsv; 0: zcgbsvx (eps tolerance); 1: zgbsvx without
+// equilibration.  Extra right hand sides (the integral-constraint columns) are just more pencils
+// here: every pencil has the same operator.  Returns 0 when done, 1 when this shape / mode has
+// no kernel (the caller then uses the general kernels at km = kn = 0), < 0 on error.
+int invert00_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
+                      const int *d_index, cplx *d_state, size_t fs, size_t ps, int nextra, cplx *d_extra,
+                      int *d_ipiv, int *d_info, int *d_iters, cudaStream_t stream)
+{
+    Ctx00 C;
+    int rc = prepare00(op, phi, mode >= 0, C, stream);
+    if (rc == -1) return 1;
+    if (rc) return rc;
+    if (mode >= 0 && (!C.tpp || nextra > 0 || aiter < 1 || dmax < 0)) return 1;
+    const int N = C.N, n = C.n;
+    if (mode == 1) { aiter = 1; dmax = 5; }
+    // workspace of the refinement: b, r | res, lastres | diter, cont, info2 | count; zgbsv with extra
+    // right hand sides only needs an info array for them
+    const size_t nb = mode >= 0 ? (size_t) npencil * N * sizeof(cplx) : 0;
+    const size_t nd = mode >= 0 ? (((size_t) npencil * sizeof(double)) + 15) & ~(size_t) 15 : 0;
+    const size_t ni = (((size_t) npencil * std::max(1, nextra) * sizeof(int)) + 15) & ~(size_t) 15;
+    const size_t need = 2 * nb + 2 * nd + 3 * ni + 16;
+    if (need > op->refine_bytes) {
+        if (op->d_refine) SZB_CUDA_OK(cudaFree(op->d_refine));
+        op->d_refine = nullptr; op->refine_bytes = 0;
+        SZB_CUDA_OK(cudaMalloc(&op->d_refine, need));
+        op->refine_bytes = need;
+    }
+    unsigned char *w = static_cast<unsigned char *>(op->d_refine);
+    cplx *B = reinterpret_cast<cplx *>(w); w += nb;
+    cplx *R = reinterpret_cast<cplx *>(w); w += nb;
+    double *res = reinterpret_cast<double *>(w); w += nd;
+    double *lastres = reinterpret_cast<double *>(w); w += nd;
+    int *diter = reinterpret_cast<int *>(w); w += ni;
+    int *cont = reinterpret_cast<int *>(w); w += ni;
+    int *info2 = reinterpret_cast<int *>(w); w += ni;
+    int *count = reinterpret_cast<int *>(w);
+
+    if (mode >= 0) {
+        gather00_kernel<<<npencil, 128, 0, stream>>>(npencil, N, n, d_index, d_state, fs, ps, B, lastres, mode ? 3.0 : 0.0);
+        count_launch();
+    }
+    // x = (LU)^-T b, in place in the state
+    if ((rc = solve00(op, C, npencil, d_index, d_state, fs, ps, 1, d_ipiv, d_info, stream))) return rc;
+    if (mode < 0) {
+        if (nextra > 0 &&
+            (rc = solve00(op, C, npencil * nextra, nullptr, d_extra, (size_t) n, (size_t) N, 1, nullptr, info2, stream)))
+            return rc;
+        if (d_iters) SZB_CUDA_OK(cudaMemsetAsync(d_iters, 0, sizeof(int) * (size_t) npencil, stream));
+        return 0;
+    }
+    Residual00Args A;
+    A.N = N; A.n = n; A.npencil = npencil; A.papt = C.papt;
+    A.index = d_index; A.x = d_state; A.fs = fs; A.ps = ps; A.b = B; A.r = R;
+    A.with_bc = 1; A.wall_begin = op->iso.enforce_lower ? 0 : 1; A.wall_end = op->iso.enforce_upper ? 2 : 1;
+    A.add = 0; A.it = 0; A.aiter = aiter; A.dmax = dmax; A.mode = mode;
+    A.tol = 2.220446049250313e-16 * 0.5;                  // dlamch('E')
+    A.res = res; A.lastres = lastres; A.diter = diter; A.cont = cont; A.count = count;
+    auto residual = [&]() -> int {
+        SZB_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int), stream));
+        auto go = [&](auto kern, size_t smem, int nt) -> int {
+            if (smem > 48 * 1024)
+                SZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            kern<<<(npencil + nt - 1) / nt, nt, smem, stream>>>(A);
+            return 0;
+        };
+        const int r2 = C.KL == 14 ? go(residual00_kernel<14>, Res00<14>::smem, 32 * Res00<14>::NW)
+                     : C.KL == 24 ? go(residual00_kernel<24>, Res00<24>::smem, 32 * Res00<24>::NW)
+                     : C.KL == 34 ? go(residual00_kernel<34>, Res00<34>::smem, 32 * Res00<34>::NW)
+                                  : go(residual00_kernel<44>, Res00<44>::smem, 32 * Res00<44>::NW);
+        if (r2) return r2;
+        count_launch();
+        SZB_CUDA_OK(cudaGetLastError());
         return 0;
     };
-    rc = fwp == 1 ? go(solve00_kernel<1, 1>) : fwp == 2 ? go(solve00_kernel<2, 1>)
-       : bwp == 1 ? go(solve00_kernel<3, 1>) : go(solve00_kernel<3, 2>);
-    if (rc) return rc;
+    if ((rc = residual())) return rc;
+    for (int it = 1; it <= dmax; ++it) {
+        int nact = 0;
+        SZB_CUDA_OK(cudaMemcpyAsync(&nact, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA_OK(cudaStreamSynchronize(stream));
+        if (nact == 0) break;
+        // d = (LU)^-T r, in place in R (field stride n, pencil stride N), every pencil; the residual
+        // kernel only takes the corrections of the pencils that go on
+        if ((rc = solve00(op, C, npencil, nullptr, R, (size_t) n, (size_t) N, 0, nullptr, info2, stream))) return rc;
+        A.add = 1; A.it = it;
+        if ((rc = residual())) return rc;
     }
+    finish00_kernel<<<(npencil + 255) / 256, 256, 0, stream>>>(npencil, d_info, diter, d_iters);
     count_launch();
     SZB_CUDA_OK(cudaGetLastError());
     return 0;

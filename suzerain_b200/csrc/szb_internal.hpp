@@ -37,8 +37,9 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                             int *d_iters, cudaStream_t stream);
-int invert00_dispatch(const szb_imexop *op, const double phi[2], int npencil, const int *d_index,
-                      cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info, cudaStream_t stream);
+int invert00_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
+                      const int *d_index, cplx *d_state, size_t fs, size_t ps, int nextra, cplx *d_extra,
+                      int *d_ipiv, int *d_info, int *d_iters, cudaStream_t stream);
 int invert_blocked_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,

@@ -649,3 +649,43 @@ def test_reuse_and_siter_hints_stay_within_the_reference_chain(dev, text):
     # per pencil, the device result satisfies the system at least as well as the reference chain's
     fresh = P.invert_spec(case.phi, case.km, case.kn, x, method="zcgbsvx", rowlen=1, nthreads=2)
     assert pc.relmax(got["x"], fresh["x"]) <= TOL
+
+
+@pytest.mark.parametrize("casename", ["tiny", "ch96"])
+def test_rhome_y_refinement_and_extra_right_hand_sides(dev, request, casename):
+    """Under linearize::rhome_y every pencil shares one factorisation: zcgbsvx / zgbsvx refine around
+    it, and the integral-constraint columns are simply more right hand sides."""
+    import torch
+    import suzerain_b200 as sz
+    case = request.getfixturevalue(casename)
+    P = pc.oracle_problem(case, "ref")
+    npen = len(case.km)
+    x = case.x.reshape(npen, -1)
+    want = P.invert00(case.phi, x)
+    assert want["info"] == 0
+    op = pc.make_imexop(case).set_linearization("rhome_y")
+    km = torch.from_numpy(case.km).to(dev)
+    kn = torch.from_numpy(case.kn).to(dev)
+    for text in ("zcgbsvx", "zgbsvx,equil=false", "zcgbsvx,aiter=2,diter=3"):
+        st = torch.from_numpy(case.x.copy()).to(dev)
+        info = torch.full((npen,), -7, dtype=torch.int32, device=dev)
+        iters = torch.full((npen,), -7, dtype=torch.int32, device=dev)
+        op.invert_batch(sz.SolverSpec.parse(text), case.phi, km, kn, st, info=info, iters=iters)
+        torch.cuda.synchronize()
+        assert np.all(info.cpu().numpy() == 0), text
+        it = iters.cpu().numpy()
+        assert it.min() >= 0 and it.max() <= 5, (text, it.min(), it.max())
+        assert pc.relmax(st.cpu().numpy().reshape(npen, -1), want["x"]) <= TOL, text
+    # extra right hand sides with zgbsv
+    rng = np.random.default_rng(9)
+    nextra = 3
+    extra = rng.standard_normal((npen, nextra, 5 * case.n)) + 1j * rng.standard_normal((npen, nextra, 5 * case.n))
+    wex = P.invert00(case.phi, extra.reshape(npen * nextra, -1))["x"].reshape(extra.shape)
+    st = torch.from_numpy(case.x.copy()).to(dev)
+    ex = torch.from_numpy(extra.copy()).to(dev)
+    info = torch.full((npen,), -7, dtype=torch.int32, device=dev)
+    op.invert_batch(sz.SolverSpec(method="zgbsv"), case.phi, km, kn, st, extra=ex, info=info)
+    torch.cuda.synchronize()
+    assert np.all(info.cpu().numpy() == 0)
+    assert pc.relmax(st.cpu().numpy().reshape(npen, -1), want["x"]) <= TOL
+    assert pc.relmax(ex.cpu().numpy(), wex) <= TOL
