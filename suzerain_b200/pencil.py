@@ -104,8 +104,11 @@ class PencilGrid:
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         self.exchange = "p2p" if int(t.item()) == 1 else "nccl"
 
-    def _p2p_setup(self, device):
-        """Symmetric buffers of every rank: fft = [max Yloc][dNz][X], wave = [max Zloc][X][Y] complex."""
+    def _p2p_setup(self, device, nfields=1):
+        """Symmetric buffers of every rank, per field: fft = [max Yloc][dNz][X], wave = [max Zloc][X][Y]
+        complex.  Re-made (collectively) when more fields per exchange are asked for than last time."""
+        if self._p2p is not None and self._p2p["nf"] < nfields:
+            self._p2p = None
         if self._p2p is None:
             import torch
             import torch.distributed as dist
@@ -115,12 +118,14 @@ class PencilGrid:
             ymax = max((r + 1) * Ny // R - r * Ny // R for r in range(R))
             zmax = max((r + 1) * dNz // R - r * dNz // R for r in range(R))
             group = self.group if self.group is not None else dist.group.WORLD
-            fft = symm.empty(2 * ymax * dNz * nxw, dtype=torch.float64, device=device)
-            wave = symm.empty(2 * zmax * nxw * Ny, dtype=torch.float64, device=device)
+            nf = max(1, int(nfields))
+            sf, sw = 2 * ymax * dNz * nxw, 2 * zmax * nxw * Ny           # doubles per field
+            fft = symm.empty(nf * sf, dtype=torch.float64, device=device)
+            wave = symm.empty(nf * sw, dtype=torch.float64, device=device)
             hf, hw = symm.rendezvous(fft, group), symm.rendezvous(wave, group)
-            pf = (C.c_ulonglong * R)(*[int(p) for p in hf.buffer_ptrs])
-            pw = (C.c_ulonglong * R)(*[int(p) for p in hw.buffer_ptrs])
-            self._p2p = dict(fft=fft, wave=wave, hf=hf, hw=hw, pf=pf, pw=pw)
+            pf = [(C.c_ulonglong * R)(*[int(p) + 8 * f * sf for p in hf.buffer_ptrs]) for f in range(nf)]
+            pw = [(C.c_ulonglong * R)(*[int(p) + 8 * f * sw for p in hw.buffer_ptrs]) for f in range(nf)]
+            self._p2p = dict(nf=nf, sf=sf, sw=sw, fft=fft, wave=wave, hf=hf, hw=hw, pf=pf, pw=pw)
         return self._p2p
 
     def __del__(self):
@@ -192,50 +197,70 @@ class PencilGrid:
 
     def transform_wave_to_physical(self, buf, stream=None):
         """pencil_grid::transform_wave_to_physical (pencil_grid.hpp:200-205), in place."""
-        import torch.distributed as dist
-        self._check(buf)
-        self._resolve_exchange(buf.device)
-        L, h, s = load(), c_void_p(self._h), self._stream(stream)
-        if self.nranks == 1:
-            rc = L.szb_pencil_grid_transform_wave_to_physical(h, c_void_p(buf.data_ptr()), s)
-        elif self.exchange == "p2p":
-            P = self._p2p_setup(buf.device)
-            P["hf"].barrier(channel=0)                      # every peer's FFT buffer is free again
-            rc = L.szb_pencil_grid_w2p_pack_peers(h, c_void_p(buf.data_ptr()), P["pf"], s)
-            P["hf"].barrier(channel=1)                      # every block has landed
-            if rc == 0:
-                rc = L.szb_pencil_grid_w2p_fft(h, c_void_p(P["fft"].data_ptr()), c_void_p(buf.data_ptr()), s)
-        else:
-            send, recv, ns, nr = self._exchange_buffers(0, buf.device)
-            rc = L.szb_pencil_grid_w2p_pack(h, c_void_p(buf.data_ptr()), c_void_p(send.data_ptr()), s)
-            if rc == 0:
-                self._all_to_all(recv, send, nr, ns)
-                rc = L.szb_pencil_grid_w2p_finish(h, c_void_p(recv.data_ptr()), c_void_p(buf.data_ptr()), s)
-        if rc:
-            raise RuntimeError(f"transform_wave_to_physical failed: {rc}")
+        self.transform_wave_to_physical_many([buf], stream)
 
     def transform_physical_to_wave(self, buf, stream=None):
         """pencil_grid::transform_physical_to_wave (pencil_grid.hpp:216-221), in place."""
-        import torch.distributed as dist
-        self._check(buf)
-        self._resolve_exchange(buf.device)
+        self.transform_physical_to_wave_many([buf], stream)
+
+    def transform_wave_to_physical_many(self, bufs, stream=None):
+        """Several fields at once (the nonlinear operator transforms 5 + 12 of them per substep,
+        navier_stokes.hpp:320-331): with the peer-memory exchange the fields share one pair of barriers."""
+        for b in bufs:
+            self._check(b)
+        dev = bufs[0].device
+        self._resolve_exchange(dev)
         L, h, s = load(), c_void_p(self._h), self._stream(stream)
+        rc = 0
         if self.nranks == 1:
-            rc = L.szb_pencil_grid_transform_physical_to_wave(h, c_void_p(buf.data_ptr()), s)
+            for b in bufs:
+                rc = rc or L.szb_pencil_grid_transform_wave_to_physical(h, c_void_p(b.data_ptr()), s)
         elif self.exchange == "p2p":
-            P = self._p2p_setup(buf.device)
-            rc = L.szb_pencil_grid_p2w_fft(h, c_void_p(buf.data_ptr()), c_void_p(P["fft"].data_ptr()), s)
-            P["hw"].barrier(channel=0)                      # every peer's wave buffer is free again
-            if rc == 0:
-                rc = L.szb_pencil_grid_p2w_scatter_peers(h, c_void_p(P["fft"].data_ptr()), P["pw"], s)
+            P = self._p2p_setup(dev, len(bufs))
+            P["hf"].barrier(channel=0)                      # every peer's FFT buffers are free again
+            for f, b in enumerate(bufs):
+                rc = rc or L.szb_pencil_grid_w2p_pack_peers(h, c_void_p(b.data_ptr()), P["pf"][f], s)
+            P["hf"].barrier(channel=1)                      # every block has landed
+            for f, b in enumerate(bufs):
+                rc = rc or L.szb_pencil_grid_w2p_fft(h, c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]),
+                                                     c_void_p(b.data_ptr()), s)
+        else:
+            send, recv, ns, nr = self._exchange_buffers(0, dev)
+            for b in bufs:
+                rc = rc or L.szb_pencil_grid_w2p_pack(h, c_void_p(b.data_ptr()), c_void_p(send.data_ptr()), s)
+                if rc == 0:
+                    self._all_to_all(recv, send, nr, ns)
+                    rc = L.szb_pencil_grid_w2p_finish(h, c_void_p(recv.data_ptr()), c_void_p(b.data_ptr()), s)
+        if rc:
+            raise RuntimeError(f"transform_wave_to_physical failed: {rc}")
+
+    def transform_physical_to_wave_many(self, bufs, stream=None):
+        for b in bufs:
+            self._check(b)
+        dev = bufs[0].device
+        self._resolve_exchange(dev)
+        L, h, s = load(), c_void_p(self._h), self._stream(stream)
+        rc = 0
+        if self.nranks == 1:
+            for b in bufs:
+                rc = rc or L.szb_pencil_grid_transform_physical_to_wave(h, c_void_p(b.data_ptr()), s)
+        elif self.exchange == "p2p":
+            P = self._p2p_setup(dev, len(bufs))
+            for f, b in enumerate(bufs):
+                rc = rc or L.szb_pencil_grid_p2w_fft(h, c_void_p(b.data_ptr()), c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]), s)
+            P["hw"].barrier(channel=0)                      # every peer's wave buffers are free again
+            for f, b in enumerate(bufs):
+                rc = rc or L.szb_pencil_grid_p2w_scatter_peers(h, c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]), P["pw"][f], s)
             P["hw"].barrier(channel=1)
             nx, ny, nz = self.local_wave_extent
-            buf[:2 * nx * ny * nz].copy_(P["wave"][:2 * nx * ny * nz])
+            for f, b in enumerate(bufs):
+                b[:2 * nx * ny * nz].copy_(P["wave"][f * P["sw"]:f * P["sw"] + 2 * nx * ny * nz])
         else:
-            send, recv, ns, nr = self._exchange_buffers(1, buf.device)
-            rc = L.szb_pencil_grid_p2w_start(h, c_void_p(buf.data_ptr()), c_void_p(send.data_ptr()), s)
-            if rc == 0:
-                self._all_to_all(recv, send, nr, ns)
-                rc = L.szb_pencil_grid_p2w_unpack(h, c_void_p(recv.data_ptr()), c_void_p(buf.data_ptr()), s)
+            send, recv, ns, nr = self._exchange_buffers(1, dev)
+            for b in bufs:
+                rc = rc or L.szb_pencil_grid_p2w_start(h, c_void_p(b.data_ptr()), c_void_p(send.data_ptr()), s)
+                if rc == 0:
+                    self._all_to_all(recv, send, nr, ns)
+                    rc = L.szb_pencil_grid_p2w_unpack(h, c_void_p(recv.data_ptr()), c_void_p(b.data_ptr()), s)
         if rc:
             raise RuntimeError(f"transform_physical_to_wave failed: {rc}")

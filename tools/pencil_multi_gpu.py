@@ -56,10 +56,28 @@ field_bytes = 8 * dNx * Ny * dNz                       # one real field, global
 out["grid"] = [dNx, Ny, dNz]
 out["exchange"] = pg.exchange
 out["ms_five_fields"] = {"wave_to_physical": w2p, "physical_to_wave": p2w}
+w2pm = timed(lambda: pg.transform_wave_to_physical_many(bufs))
+p2wm = timed(lambda: pg.transform_physical_to_wave_many(bufs))
+out["ms_five_fields_one_exchange"] = {"wave_to_physical": w2pm, "physical_to_wave": p2wm}
 # algorithmic traffic of one transform: read the wave field, write the physical field (or back)
 nxw = dNx // 2 + 1
 alg = 5 * (16 * nxw * Ny * dNz + field_bytes)
 out["algorithmic_GB/s_aggregate"] = {"wave_to_physical": alg / w2p / 1e6, "physical_to_wave": alg / p2w / 1e6}
+ref = [b.clone() for b in bufs]
+for b in bufs:
+    pg.transform_physical_to_wave(b)          # make the buffers valid wave data of real fields
+wave0 = [b.clone() for b in bufs]
+pg.transform_wave_to_physical_many(bufs)
+pg.transform_physical_to_wave_many(bufs)
+torch.cuda.synchronize()
+nx, ny, nz = pg.local_wave_extent
+err = max(float((b[:2 * nx * ny * nz] / (dNx * dNz) - w[:2 * nx * ny * nz]).abs().max() / w[:2 * nx * ny * nz].abs().max())
+          for b, w in zip(bufs, wave0)) if nx * ny * nz else 0.0
+t = torch.tensor([err], dtype=torch.float64, device=dev)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+out["many_round_trip_relmax"] = float(t)
+assert float(t) <= 1e-12, out
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
