@@ -689,3 +689,36 @@ def test_rhome_y_refinement_and_extra_right_hand_sides(dev, request, casename):
     assert np.all(info.cpu().numpy() == 0)
     assert pc.relmax(st.cpu().numpy().reshape(npen, -1), want["x"]) <= TOL
     assert pc.relmax(ex.cpu().numpy(), wex) <= TOL
+
+
+def test_rhome_y_warp_per_pencil_fallback_matches_reference(dev):
+    """The warp-per-pencil sweeps (shapes the thread-per-pencil kernel has no instantiation for) are
+    selected by SZB_RHOME_Y_WARP, read once per process: run them in a child process."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "tests")
+import parity_common as pc, suzerain_b200 as sz
+case = pc.make_case("tiny_16x24x16")
+P = pc.oracle_problem(case, "ref")
+npen = len(case.km)
+want = P.invert00(case.phi, case.x.reshape(npen, -1), want_ipiv=True)
+op = pc.make_imexop(case).set_linearization("rhome_y")
+dev = torch.device("cuda:0")
+st = torch.from_numpy(case.x.copy()).to(dev)
+km = torch.from_numpy(case.km).to(dev); kn = torch.from_numpy(case.kn).to(dev)
+ipiv = torch.zeros((npen, op.N), dtype=torch.int32, device=dev)
+info = torch.full((npen,), -7, dtype=torch.int32, device=dev)
+op.invert_batch(sz.SolverSpec(method="zgbsv"), case.phi, km, kn, st, ipiv=ipiv, info=info)
+torch.cuda.synchronize()
+assert np.all(info.cpu().numpy() == 0)
+assert np.array_equal(ipiv.cpu().numpy(), np.tile(want["ipiv"], (npen, 1)))
+err = pc.relmax(st.cpu().numpy().reshape(npen, -1), want["x"])
+assert err <= 1e-12, err
+print("ok", err)
+'''
+    import os
+    env = dict(os.environ, SZB_RHOME_Y_WARP="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=pc.ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
