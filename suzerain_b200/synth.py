@@ -72,6 +72,27 @@ def reference_profiles(y, Ly=2.0, scenario=SCENARIO, one_sided=False, seed=SEED)
     return np.ascontiguousarray(refs)
 
 
+def reference_profiles_from_means(rho, u, v, w, T, mu, scenario=SCENARIO):
+    """The 26 quantities from pointwise MEAN profiles of a state without fluctuations (the one-dimensional
+    restart files of the reference: second moments are products of means), same formulas as above."""
+    g, Ma = scenario["gamma"], scenario["Ma"]
+    rho, u, v, w, T, mu = (np.asarray(a, dtype=np.float64) for a in (rho, u, v, w, T, mu))
+    uu, vv, ww, uv, uw, vw = u * u, v * v, w * w, u * v, u * w, v * w
+    u2 = uu + vv + ww
+    p = rho * T / g
+    m = np.stack([rho * u, rho * v, rho * w])
+    e = p / (g - 1) + 0.5 * Ma * Ma * rho * u2
+    nu = mu / rho
+    e_gradrho = ((g - 2) * e - 2 * p) / (rho * rho) * m
+    e_divm = (e + p) / rho
+    e_deltarho = mu / (rho * rho) * ((g - 1) * e - 2 * p)
+    refs = np.stack([
+        u, v, w, u2, uu, uv, uw, vv, vw, ww,
+        nu, nu * u, nu * v, nu * w, nu * u2, nu * uu, nu * uv, nu * uw, nu * vv, nu * vw, nu * ww,
+        e_gradrho[0], e_gradrho[1], e_gradrho[2], e_divm, e_deltarho])
+    return np.ascontiguousarray(refs)
+
+
 def isothermal_walls(one_sided=False):
     """specification_isothermal-like wall data: (enforce_lower, enforce_upper, lower, upper)
     with lower/upper = (T, u, v, w)."""

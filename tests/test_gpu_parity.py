@@ -722,3 +722,18 @@ print("ok", err)
     env = dict(os.environ, SZB_RHOME_Y_WARP="1")
     r = subprocess.run([sys.executable, "-c", code], cwd=pc.ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", ["channel_k08", "coleman3k01.00"])
+def test_reference_restart_state_and_profiles(dev, name):
+    """Grid, scenario, mean profiles and mean state of the reference's own restart files
+    (fields/channel_k08.h5: Ny=96, k=8, htdelta=3 -- the bench grid; fields/coleman3k01.00.h5: Ny=128)."""
+    case = pc.make_case_from_restart(name)
+    got = pc.gpu_accumulate(case, dev)
+    assert pc.relmax(got, pc.oracle_accumulate(case, kind="ref")) <= TOL
+    for solver in ("zgbsv", "zcgbsvx"):
+        got = pc.gpu_invert(case, solver, dev)
+        want = pc.oracle_invert(case, solver, kind="ref")
+        assert want["info"] == 0 and np.all(got["info"] == 0)
+        assert np.array_equal(got["ipiv"], want["ipiv"]), "pivot choices differ"
+        assert pc.relmax(got["x"], want["x"]) <= TOL

@@ -1,0 +1,90 @@
+"""Fixtures extracted from the reference's own restart files (fields/*.h5: written by the real
+reference build with GSL B-splines through ESIO/HDF5; tests/golden/make_restart_golden.py).
+
+These pin SURVEY 8a rows 15-16 (the B-spline collocation operators, the htstretch grid, the Greville
+points) against actual reference OUTPUTS on production-like grids -- orders 6..9, Ny 32..288,
+two-sided and one-sided stretching -- rather than against a restatement."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "restart_fixtures.npz"))
+NAMES = [str(n) for n in GOLD["names"]]
+EPS = np.finfo(float).eps
+
+
+def gold(name, key):
+    return GOLD[f"{name}/{key}"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_product_bspline_operators_match_the_references_stored_operators(name):
+    import suzerain_b200 as sz
+    k, Ny, ht, Ly = int(gold(name, "k")), int(gold(name, "Ny")), float(gold(name, "htdelta")), float(gold(name, "Ly"))
+    bp = gold(name, "breakpoints_y")
+    # support::create_bsplines (support.cpp:288-311): the stretched breakpoints themselves
+    assert np.abs(sz.htstretch_breakpoints(Ny, k, 0.0, Ly, ht) - bp).max() <= 4 * EPS * Ly
+    bop = sz.BsplineOp.from_breakpoints(k, bp)
+    assert (bop.n, bop.max_kl, bop.max_ku) == (Ny, int(gold(name, "kl")), int(gold(name, "ku")))
+    assert np.abs(bop.greville() - gold(name, "collocation_points_y")).max() <= 4 * EPS * Ly
+    for d in range(3):
+        want = gold(name, f"Dy{d}T")
+        got = np.asarray(bop.storage[d])
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 5e-13 * np.abs(want).max(), (name, d)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_bspline_operators_match_the_references_stored_operators(name):
+    pytest.importorskip("scipy")
+    from oracle import bspline as obs
+    k = int(gold(name, "k"))
+    a = obs.make_bsplineop(k, gold(name, "breakpoints_y"))
+    assert np.abs(a.knots - gold(name, "knots")).max() == 0.0
+    for d in range(3):
+        want = gold(name, f"Dy{d}T")
+        assert np.abs(a.storage[d] - want).max() <= 5e-13 * np.abs(want).max(), (name, d)
+
+
+def test_restart_mean_state_is_consistent_with_its_profiles():
+    """Restart files hold collocation-point VALUES (support::save_collocation_values): for these
+    one-dimensional mean states the (0,0) mode of rho is the stored mean profile itself, and the
+    B-spline coefficients follow from the mass matrix D0 (a check of the fixture extraction and of the
+    operator orientation)."""
+    import suzerain_b200 as sz
+    for name in [str(n) for n in GOLD["state_names"]]:
+        vals = gold(name, "rho")
+        assert np.abs(vals.imag).max() == 0.0
+        assert np.array_equal(vals.real, gold(name, "bar_rho")[0]), name
+        bop = sz.BsplineOp.from_breakpoints(int(gold(name, "k")), gold(name, "breakpoints_y"))
+        D0 = bop.dense(0)
+        coef = np.linalg.solve(D0, vals.real)
+        assert np.abs(D0 @ coef - vals.real).max() <= 1e-13 * np.abs(vals).max()
+        # momentum over density is the stored mean velocity up to the sampling window (bar_* are running means)
+        u = gold(name, "rho_u").real / vals.real
+        assert np.abs(u - gold(name, "bar_u")[0]).max() <= 2e-3 * np.abs(u).max(), name
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/fields"), reason="reference tree not present")
+def test_h5lite_reads_every_reference_restart_file():
+    import glob
+    from suzerain_b200.h5lite import H5File
+    files = sorted(glob.glob("/root/reference/fields/*.h5"))
+    assert len(files) >= 20
+    for p in files:
+        f = H5File(p)
+        assert {"Ny", "k", "rho", "rho_E"} <= set(f.keys())
+        Ny = int(f["Ny"][0])
+        if "breakpoints_y" in f:                                      # absent from the oldest legacy file
+            assert f["breakpoints_y"].shape == (Ny - int(f["k"][0]) + 2,)
+        assert f["rho"].shape[-2:] == (Ny, 2)                         # complex = double[2] array datatype
+    # the committed fixture equals a fresh read
+    f = H5File("/root/reference/fields/channel_k08.h5")
+    assert np.array_equal(f["Dy1T"], gold("channel_k08", "Dy1T"))
+    assert f.attrs("Dy1T")["kl"][0] == 6
