@@ -432,11 +432,12 @@ class OperatorHybridIsothermalDevice:
         return self.op.accumulate_batch(phi, self.km, self.kn, state, 0.0, state,
                                         index=self.active, stream=stream)
 
-    def accumulate_mass_plus_scaled_operator(self, phi, input, beta, output, stream=None):
-        """output: contiguous state (5, npencil, Ny) (suzerain/storage.hpp:267-268)."""
+    def accumulate_mass_plus_scaled_operator(self, phi, input, beta, output, stream=None, interleaved_output=False):
+        """output: contiguous state (5, npencil, Ny) (suzerain/storage.hpp:267-268) as in the reference, or
+        -- for a device-resident stepper that swaps the two buffers -- interleaved like the input."""
         n = self.op.n
-        return self.op.accumulate_batch(phi, self.km, self.kn, input, beta, output,
-                                        index=self.active, y_strides=(n * self.npencil, n),
+        return self.op.accumulate_batch(phi, self.km, self.kn, input, beta, output, index=self.active,
+                                        y_strides=None if interleaved_output else (n * self.npencil, n),
                                         stream=stream)
 
     def invert_mass_plus_scaled_operator(self, phi, state, stream=None, ipiv=None, iters=None):
