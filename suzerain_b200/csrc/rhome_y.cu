@@ -443,29 +443,32 @@ struct Tpp {
     static constexpr int XRY = YA + PD + 2;            // ring, in collocation points
     static constexpr int XR = 5 * XRY;                 // ring, in rows
     static constexpr int TS = 5 * KV + 15;             // one block of the factors (forward; backward is smaller)
-    static constexpr int NW = (sizeof(cplx) * (4 * 32 * XR + 2 * TS) + 1024 <= 227 * 1024) ? 4 : 3;
-    static constexpr size_t smem = sizeof(cplx) * ((size_t) NW * 32 * XR + 2 * TS);
+    // NW groups of 32 pencils per CTA, two warps per group (they split the rows of every step)
+    static constexpr int NW = (sizeof(cplx) * (4 * 32 * (XR + 5) + 2 * TS) + 1024 <= 227 * 1024) ? 4 : 3;
+    static constexpr size_t smem = sizeof(cplx) * ((size_t) NW * 32 * (XR + 5) + 2 * TS);
 };
 
 template <int KV, int KL>
-__global__ void __launch_bounds__(32 * Tpp<KV, KL>::NW)
+__global__ void __launch_bounds__(64 * Tpp<KV, KL>::NW)
 solve00_tpp_kernel(const Solve00Args A)
 {
     using T = Tpp<KV, KL>;
-    constexpr int YA = T::YA, YB = T::YB, XRY = T::XRY, XR = T::XR, TS = T::TS, NW = T::NW, NT = 32 * NW;
+    constexpr int YA = T::YA, YB = T::YB, XRY = T::XRY, XR = T::XR, TS = T::TS, NW = T::NW, NT = 64 * NW, NP = 32 * NW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = A.n, N = A.N;
-    const int p = blockIdx.x * NT + tid;
-    const bool active = p < A.npencil;
+    const int group = warp % NW, half = warp / NW;               // the two warps of a group share its ring
+    const int p = blockIdx.x * NP + group * 32 + lane;
+    const bool active = p < A.npencil, lead = half == 0;
     const int info = *A.info1;
-    if (active) A.info_out[p] = info;
+    if (active && lead) A.info_out[p] = info;
     if (A.ipiv_out) {
-        const int base = blockIdx.x * NT, cnt = max(0, min(NT, A.npencil - base)) * N;
+        const int base = blockIdx.x * NP, cnt = max(0, min(NP, A.npencil - base)) * N;
         for (int e = tid; e < cnt; e += NT) A.ipiv_out[(size_t) base * N + e] = A.ipiv[e % N];
     }
     if (info) return;
     cplx *tab = reinterpret_cast<cplx *>(smem_raw);                               // [2][TS]
-    cplx *ring = tab + 2 * TS + (size_t) warp * 32 * XR + lane;                   // row r of this lane: ring[(r % XR) * 32]
+    cplx *ring = tab + 2 * TS + (size_t) group * 32 * (XR + 5) + lane;            // row r of this lane: ring[(r % XR) * 32]
+    cplx *part = ring + (size_t) XR * 32;                                         // [5][32] partial dot products (backward)
     cplx *v = A.state + (A.index ? (size_t) A.index[active ? p : 0] : (size_t) (active ? p : 0)) * A.ps;
     const size_t fs = A.fs;
     const bool bc_lo = A.with_bc && A.wall_begin == 0, bc_hi = A.with_bc && A.wall_end == 2;
@@ -476,7 +479,7 @@ solve00_tpp_kernel(const Solve00Args A)
     };
     // collocation point y -> its five ring rows (XR is a multiple of five: a point never wraps)
     auto request = [&](int y, bool forward) {
-        if (y < 0) return;
+        if (y < 0 || !lead) return;
         cplx *d = ring + (size_t) (y % XRY) * 5 * 32;
         const bool wall = forward && ((y == 0 && bc_lo) || (y == n - 1 && bc_hi));
 #pragma unroll
@@ -486,7 +489,7 @@ solve00_tpp_kernel(const Solve00Args A)
         }
     };
     auto release = [&](int y) {        // ring -> state
-        if (y >= 0 && y < n && active) {
+        if (y >= 0 && y < n && active && lead) {
             const cplx *d = ring + (size_t) (y % XRY) * 5 * 32;
 #pragma unroll
             for (int f = 0; f < 5; ++f) v[(size_t) f * fs + y] = d[f * 32];
@@ -530,7 +533,7 @@ solve00_tpp_kernel(const Solve00Args A)
         // four rows at a time: loads first, the twenty products interleaved over the rows, stores last
         static_assert(KV % 4 == 0, "rows are taken in fours");
 #pragma unroll 2
-        for (int i = 0; i < KV; i += 4) {
+        for (int i = 4 * half; i < KV; i += 8) {
             cplx *px[4], w[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -551,7 +554,7 @@ solve00_tpp_kernel(const Solve00Args A)
 #pragma unroll
             for (int g = 0; g < 4; ++g) *px[g] = w[g];
         }
-        if (active) {
+        if (active && lead) {
             v[b] = y0; v[fs + b] = y1; v[2 * fs + b] = y2; v[3 * fs + b] = y3; v[4 * fs + b] = y4;
         }
         s0 += 5; s0 -= s0 >= XR ? XR : 0;
@@ -569,23 +572,29 @@ solve00_tpp_kernel(const Solve00Args A)
         s0 = (b % XRY) * 5;
         cplx *r0 = ring + (size_t) s0 * 32;
         const cplx *tri = tab + (b & 1) * TS, *lp = tri + 15;
-        if (A.plain[b]) {
+        const bool plain = A.plain[b];
+        if (plain) {
             cplx a0(0.0, 0.0), a1(0.0, 0.0), a2(0.0, 0.0), a3(0.0, 0.0), a4(0.0, 0.0);
-#pragma unroll 4
-            for (int i = 0; i < KL; ++i) {
+#pragma unroll 2
+            for (int i = half; i < KL; i += 2) {
                 int sl = s0 + 5 + i; sl -= sl >= XR ? XR : 0;
                 const cplx xv = ring[(size_t) sl * 32];
                 addmul(a0, lp[5 * i], xv); addmul(a1, lp[5 * i + 1], xv); addmul(a2, lp[5 * i + 2], xv);
                 addmul(a3, lp[5 * i + 3], xv); addmul(a4, lp[5 * i + 4], xv);
             }
-            const cplx x4 = r0[128] - a4;
-            cplx x3 = r0[96] - a3; submul(x3, tri[9], x4);
-            cplx x2 = r0[64] - a2; submul(x2, tri[7], x3); submul(x2, tri[8], x4);
-            cplx x1 = r0[32] - a1; submul(x1, tri[4], x2); submul(x1, tri[5], x3); submul(x1, tri[6], x4);
-            cplx x0 = r0[0] - a0; submul(x0, tri[0], x1); submul(x0, tri[1], x2); submul(x0, tri[2], x3);
-            submul(x0, tri[3], x4);
-            r0[0] = x0; r0[32] = x1; r0[64] = x2; r0[96] = x3; r0[128] = x4;
-        } else {
+            if (!lead) { part[0] = a0; part[32] = a1; part[64] = a2; part[96] = a3; part[128] = a4; }
+            __syncthreads();
+            if (lead) {
+                a0 += part[0]; a1 += part[32]; a2 += part[64]; a3 += part[96]; a4 += part[128];
+                const cplx x4 = r0[128] - a4;
+                cplx x3 = r0[96] - a3; submul(x3, tri[9], x4);
+                cplx x2 = r0[64] - a2; submul(x2, tri[7], x3); submul(x2, tri[8], x4);
+                cplx x1 = r0[32] - a1; submul(x1, tri[4], x2); submul(x1, tri[5], x3); submul(x1, tri[6], x4);
+                cplx x0 = r0[0] - a0; submul(x0, tri[0], x1); submul(x0, tri[1], x2); submul(x0, tri[2], x3);
+                submul(x0, tri[3], x4);
+                r0[0] = x0; r0[32] = x1; r0[64] = x2; r0[96] = x3; r0[128] = x4;
+            }
+        } else if (lead) {
             for (int m = 4; m >= 0; --m) {
                 const int j = j0 + m;
                 if (j > N - 2) continue;
@@ -868,10 +877,11 @@ int solve00(const szb_imexop *op, const Ctx00 &C, int npencil, const int *d_inde
     A.ipiv_out = d_ipiv; A.info_out = d_info;
     int rc = 0;
     if (C.tpp) {
+        // nt pencils per CTA, two warps per group of 32
         auto go = [&](auto kern, size_t smem, int nt) -> int {
             if (smem > 48 * 1024)
                 SZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            kern<<<(npencil + nt - 1) / nt, nt, smem, stream>>>(A);
+            kern<<<(npencil + nt - 1) / nt, 2 * nt, smem, stream>>>(A);
             return 0;
         };
         rc = C.KL == 14 ? go(solve00_tpp_kernel<28, 14>, Tpp<28, 14>::smem, 32 * Tpp<28, 14>::NW)
