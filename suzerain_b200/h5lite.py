@@ -5,7 +5,8 @@ The image has neither libhdf5 nor h5py, and the reference's restart / fixture fi
 are plain "version 0 superblock" HDF5: old-style groups (symbol-table B-trees + local heaps),
 version-1 object headers, little-endian IEEE / integer atomic types, contiguous, compact or chunked
 (optionally deflate / shuffle) layouts.  That subset is what this module reads; anything else
-raises ``H5Error``.  Layout follows the public HDF5 File Format Specification (version 1.1/2.0).
+raises ``H5Error``.  (All of the reference's files are contiguous: the chunked / filter code follows the
+specification but has no fixture to exercise it.)  Layout follows the public HDF5 File Format Specification (version 1.1/2.0).
 
     f = H5File(path); f.keys(); f["Dy0T"]  -> numpy array;  f.attrs("rho")  -> dict
 """
