@@ -429,6 +429,9 @@ def run_b200(args):
                      "unit": "GB/s", "frac": inv_gbs / peak, "traffic": tr("invert_pipe"),
                      "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write per launch)",
                      "ms_per_launch": inv_ms, "algorithmic_bytes_per_launch": inv_bytes,
+                     "note": "SURVEY 8d: the fused kernel only moves the 32 N bytes of state per system (assembly, "
+                             "factors and U never touch HBM), so the HBM fraction is small by construction; the "
+                             "binding roofline is the FP64 / latency one below (see DESIGN 3.1, 4.1)",
                      "fp64_gflops_upper": lu_flop * wl.nactive / (inv_ms * 1e-3) / 1e9,
                      # the kernel is an FP64 latency chain, not an HBM stream: the second roofline
                      "fp64": {"achieved": lu_flop * wl.nactive / (inv_ms * 1e-3) / 1e12, "peak": fp64_peak,
