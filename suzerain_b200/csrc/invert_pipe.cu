@@ -893,6 +893,9 @@ int launch_pipe_vg(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t 
     SZB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, invert_pipe_kernel<W, VG>,
                                                               W::NTH, smem));
     if (per_sm < 1) return 1;
+    static const bool debug = std::getenv("SZB_PIPE_DEBUG") != nullptr;
+    if (debug)
+        std::fprintf(stderr, "invert_pipe: KL=%d N=%d vg=%d threads=%d smem=%zu CTAs/SM=%d\n", W::KL, N, (int) VG, W::NTH, smem, per_sm);
     int slots = op->sm_count * per_sm;
     if (slots > npencil) slots = npencil;
     const size_t lbytes = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
@@ -913,15 +916,17 @@ int launch_pipe_vg(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t 
     return 0;
 }
 
-// The b -> y -> x vectors (2 N complex per CTA) stay in shared memory while two CTAs still fit
-// an SM with them; beyond that (Ny >= 256 at k = 8) they move to a global scratch read at L2.
+// The b -> y -> x vectors (2 N complex per CTA) stay in shared memory while MINB CTAs still fit
+// an SM with them; beyond that (Ny >= 256 at k = 8, any Ny >= 96 at k = 6 with three CTAs per SM)
+// they move to a global scratch read at L2.
 template <class W>
 int launch_pipe(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
 {
-    const size_t two_per_sm = (233472 - 2 * 1024) / 2;
+    // shared memory available to each of the MINB CTAs the register budget is sized for
+    const size_t per_cta = (233472 - (size_t) W::MINB * 1024) / W::MINB;
     static const bool allow = [] { const char *e = std::getenv("SZB_PIPE_VG"); return !(e && e[0] == '0'); }();
-    if (allow && W::MINB >= 2 && pipe_smem_bytes<W>(op->A.N, false) > two_per_sm
-        && pipe_smem_bytes<W>(op->A.N, true) <= two_per_sm)
+    if (allow && W::MINB >= 2 && pipe_smem_bytes<W>(op->A.N, false) > per_cta
+        && pipe_smem_bytes<W>(op->A.N, true) <= per_cta)
         return launch_pipe_vg<W, true>(op, A, npencil, stream);
     return launch_pipe_vg<W, false>(op, A, npencil, stream);
 }
@@ -1111,8 +1116,8 @@ int launch_residual(const szb_imexop *op, ResidualArgs &A, cudaStream_t stream)
 int dispatch_residual(const szb_imexop *op, ResidualArgs &A, cudaStream_t stream)
 {
     switch (op->A.KL) {
-    case 14: return launch_residual<PipeCfg<14, 14, 8, 3, 1, 7, 2>>(op, A, stream);
-    case 24: return launch_residual<PipeCfg<24, 24, 16, 4, 2, 8, 2>>(op, A, stream);
+    case 14: return launch_residual<PipeCfg<14, 14, 8, 3, 1, 7, 3>>(op, A, stream);
+    case 24: return launch_residual<PipeCfg<24, 24, 16, 4, 2, 8, 3>>(op, A, stream);
     case 34: return launch_residual<PipeCfg<34, 34, 16, 6, 3, 7, 2>>(op, A, stream);
     case 44: return launch_residual<PipeCfg<44, 44, 32, 6, 2, 9, 1>>(op, A, stream);
     default: return 1;
@@ -1137,8 +1142,8 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     A.zero_wall_rhs = zero_wall_rhs;
     if (op->A.KL != op->A.KU) return 1;
     switch (op->A.KL) {
-    case 14: return launch_pipe<PipeCfg<14, 14, 8, 3, 1, 7, 2>>(op, A, npencil, stream);     // k = 4
-    case 24: return launch_pipe<PipeCfg<24, 24, 16, 4, 2, 8, 2>>(op, A, npencil, stream);    // k = 6
+    case 14: return launch_pipe<PipeCfg<14, 14, 8, 3, 1, 7, 3>>(op, A, npencil, stream);     // k = 4
+    case 24: return launch_pipe<PipeCfg<24, 24, 16, 4, 2, 8, 3>>(op, A, npencil, stream);    // k = 6
     case 34: return launch_pipe<PipeCfg<34, 34, 16, 6, 3, 7, 2>>(op, A, npencil, stream);    // k = 8
     case 44: return launch_pipe<PipeCfg<44, 44, 32, 6, 2, 9, 1>>(op, A, npencil, stream);    // k = 10
     default: return 1;
