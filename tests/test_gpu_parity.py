@@ -737,3 +737,21 @@ def test_reference_restart_state_and_profiles(dev, name):
         assert want["info"] == 0 and np.all(got["info"] == 0)
         assert np.array_equal(got["ipiv"], want["ipiv"]), "pivot choices differ"
         assert pc.relmax(got["x"], want["x"]) <= TOL
+
+
+@pytest.mark.parametrize("solver", ["zgbsv", "zcgbsvx"])
+def test_nan_right_hand_side_stays_in_its_pencil(dev, tiny, solver):
+    """SURVEY 8g-7 (dsgbsvx.def:306-310): a NaN in b makes that pencil's x all NaN; the reference reports
+    no error for it.  The other pencils of the batch must not notice."""
+    import dataclasses
+    x = tiny.x.copy()
+    bad = 3
+    x[bad, 2, 5] = np.nan
+    case = dataclasses.replace(tiny, x=x)
+    got = pc.gpu_invert(case, solver, dev)
+    want = pc.oracle_invert(case, solver, kind="ref")
+    assert np.all(got["info"] == 0) and want["info"] == 0
+    assert np.all(np.isnan(want["x"][bad])) and np.all(np.isnan(got["x"][bad].real) | np.isnan(got["x"][bad].imag))
+    ok = np.arange(len(case.km)) != bad
+    assert not np.isnan(got["x"][ok]).any()
+    assert pc.relmax(got["x"][ok], want["x"][ok]) <= TOL
