@@ -384,3 +384,20 @@ def test_reference_solver_specifications_agree_like_its_own_test():
     for scale, code in ((100, 1), (1000, 3)):
         r = P.invert_spec(case.phi * scale, case.km, case.kn, x, method="zgbsvx", equil=True)
         assert r["info"] == 0 and set(r["stats"][:, 0].astype(int)) == {code}
+
+
+def test_public_headers_are_plain_c():
+    """The drop-in boundary is a C ABI: both headers must compile as C99 and as C++11 on their own."""
+    import shutil
+    import subprocess
+    import tempfile
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = '#include "suzerain_b200.h"\n#include "suzerain_b200_fft.h"\nint main(void) { szb_zgbsv_spec s = szb_zgbsv_spec_default(); (void) s; return 0; }\n'
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "hdr.c")
+        open(p, "w").write(src)
+        inc = os.path.join(ROOT, "include")
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + inc, p], check=True)
+        if shutil.which("g++"):
+            subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, "-x", "c++", p], check=True)
