@@ -91,6 +91,8 @@ struct AccumulateArgs {
     double a[25], b[25], c[25];
     int npencil;
     int zero_wave;          // linearize::rhome_y: the operator at km = kn = 0 for every pencil
+    const int *index_out;   // slot of the output pencil when it differs from the input's (null: the same ...
+    int out_plain;          // ... or, with this flag, the pencil's own number)
 };
 
 // One output row of phi L at collocation point y, statically specialised on the equation
@@ -161,7 +163,7 @@ accumulate_kernel(const AccumulateArgs A)
     const cplx *s_in = s_inbuf + stage * 5 * np;
     const double km = A.zero_wave ? 0.0 : A.km[p], kn = A.zero_wave ? 0.0 : A.kn[p];
     const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
-    cplx *out = A.out + slot * A.out_ps;
+    cplx *out = A.out + (A.index_out ? (size_t) A.index_out[p] : A.out_plain ? (size_t) p : slot) * A.out_ps;
     if (threadIdx.x == 0 && p + (int) gridDim.x < A.npencil) fetch(p + gridDim.x, stage ^ 1);
     for (int t = threadIdx.x; t < nterms; t += blockDim.x)
         s_alpha[t] = A.phi * (wave_factor(A.terms->wave[t], km, kn) * A.terms->sc[t]);
@@ -253,6 +255,56 @@ pack_kernel(const PackArgs A)
     cplx *M = A.out + (size_t) p * A.N * A.rows + A.rowoff;
     pack_pencil(A, A.rows, A.km[p], A.kn[p], s_alpha, s_x, M);
 }
+
+// accumulate with separate pencil slots for input and output (the refinement residual writes a compact buffer)
+int accumulate_launch(const szb_imexop *op, const double phi[2],
+        int npencil, const double *d_km, const double *d_kn, const int *d_index, const int *d_index_out, int out_plain,
+        const szb_complex *d_in, size_t in_fs, size_t in_ps,
+        const double beta[2],
+        szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream)
+{
+    if (!op) return -1;
+    if (!phi) return -2;
+    if (npencil < 0) return -3;
+    if (!d_km) return -4;
+    if (!d_kn) return -5;
+    if (!d_in) return -7;
+    if (!beta) return -10;
+    if (!d_out) return -11;
+    if (npencil == 0) return 0;
+    if ((const void *) d_in == (const void *) d_out
+        && !(beta[0] == 0.0 && beta[1] == 0.0 && in_fs == out_fs && in_ps == out_ps)) return -11;
+    AccumulateArgs A;
+    A.D = op->d_D; A.refs = op->d_refs; A.terms = op->d_terms;
+    A.n = op->n; A.kl = op->kl; A.ku = op->ku; A.ld = op->ld;
+    A.phi = cplx(phi[0], phi[1]); A.beta = cplx(beta[0], beta[1]);
+    A.km = d_km; A.kn = d_kn; A.index = d_index; A.index_out = d_index_out; A.out_plain = out_plain;
+    A.in = reinterpret_cast<const cplx *>(d_in); A.in_fs = in_fs; A.in_ps = in_ps;
+    A.out = reinterpret_cast<cplx *>(d_out); A.out_fs = out_fs; A.out_ps = out_ps;
+    A.nrbc = (op->have_a ? 1 : 0) | (op->have_b ? 2 : 0) | (op->have_c ? 4 : 0);
+    std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
+    std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
+    std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
+    A.npencil = npencil;
+    A.zero_wave = op->linearization == SZB_LINEARIZE_RHOME_Y;
+    const size_t smem = sizeof(cplx) * (10 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
+    if (smem > 227 * 1024) return -1;
+    int threads = (op->n + 31) / 32 * 32;
+    if (threads > 512) threads = 512;
+    if (threads <= 128) {
+        if (smem > 48 * 1024)
+            SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        accumulate_kernel<128, 4><<<std::min(npencil, 5 * op->sm_count), threads, smem, (cudaStream_t) stream>>>(A);
+    } else {
+        if (smem > 48 * 1024)
+            SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        accumulate_kernel<512, 1><<<std::min(npencil, 2 * op->sm_count), threads, smem, (cudaStream_t) stream>>>(A);
+    }
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 
 }  // namespace szb
 
@@ -413,46 +465,8 @@ int szb_imexop_accumulate_batch(const szb_imexop *op, const double phi[2],
         const double beta[2],
         szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream)
 {
-    if (!op) return -1;
-    if (!phi) return -2;
-    if (npencil < 0) return -3;
-    if (!d_km) return -4;
-    if (!d_kn) return -5;
-    if (!d_in) return -7;
-    if (!beta) return -10;
-    if (!d_out) return -11;
-    if (npencil == 0) return 0;
-    if ((const void *) d_in == (const void *) d_out
-        && !(beta[0] == 0.0 && beta[1] == 0.0 && in_fs == out_fs && in_ps == out_ps)) return -11;
-    AccumulateArgs A;
-    A.D = op->d_D; A.refs = op->d_refs; A.terms = op->d_terms;
-    A.n = op->n; A.kl = op->kl; A.ku = op->ku; A.ld = op->ld;
-    A.phi = cplx(phi[0], phi[1]); A.beta = cplx(beta[0], beta[1]);
-    A.km = d_km; A.kn = d_kn; A.index = d_index;
-    A.in = reinterpret_cast<const cplx *>(d_in); A.in_fs = in_fs; A.in_ps = in_ps;
-    A.out = reinterpret_cast<cplx *>(d_out); A.out_fs = out_fs; A.out_ps = out_ps;
-    A.nrbc = (op->have_a ? 1 : 0) | (op->have_b ? 2 : 0) | (op->have_c ? 4 : 0);
-    std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
-    std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
-    std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
-    A.npencil = npencil;
-    A.zero_wave = op->linearization == SZB_LINEARIZE_RHOME_Y;
-    const size_t smem = sizeof(cplx) * (10 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
-    if (smem > 227 * 1024) return -1;
-    int threads = (op->n + 31) / 32 * 32;
-    if (threads > 512) threads = 512;
-    if (threads <= 128) {
-        if (smem > 48 * 1024)
-            SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        accumulate_kernel<128, 4><<<std::min(npencil, 5 * op->sm_count), threads, smem, (cudaStream_t) stream>>>(A);
-    } else {
-        if (smem > 48 * 1024)
-            SZB_CUDA_OK(cudaFuncSetAttribute(accumulate_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        accumulate_kernel<512, 1><<<std::min(npencil, 2 * op->sm_count), threads, smem, (cudaStream_t) stream>>>(A);
-    }
-    count_launch();
-    SZB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return szb::accumulate_launch(op, phi, npencil, d_km, d_kn, d_index, nullptr, 0, d_in, in_fs, in_ps, beta,
+                                  d_out, out_fs, out_ps, stream);
 }
 
 int szb_imexop_pack_batch(const szb_imexop *op, const double phi[2],

@@ -29,6 +29,9 @@ int invert_window_dispatch(const szb_imexop *op, const double phi[2], int npenci
                            const double *d_km, const double *d_kn, const int *d_index,
                            cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                            int *d_iters, cudaStream_t stream);
+int accumulate_launch(const szb_imexop *op, const double phi[2], int npencil, const double *d_km, const double *d_kn,
+                      const int *d_index, const int *d_index_out, int out_plain, const szb_complex *d_in, size_t in_fs, size_t in_ps,
+                      const double beta[2], szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream);
 int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
