@@ -8,7 +8,7 @@ where /root/reference exists; the .npz is committed, the files themselves are no
                          own collocation operators in band storage, suzerain/support/support.cpp
                          save_bsplines); for two channel files also the scenario scalars, the mean
                          profiles bar_{rho,u,T,mu} and the (0,0) mode of the five conserved fields
-                         (collocation-point values, as restart files store them).
+                         (B-spline coefficients, as restart files store them).
 
 Usage: python tests/golden/make_restart_golden.py [/root/reference]
 """

@@ -78,27 +78,31 @@ def make_case(config="tiny_16x24x16", max_pencils=None, phi=None, seed=synth.SEE
 
 def make_case_from_restart(name="channel_k08", Nx=16, Nz=16, seed=synth.SEED) -> Case:
     """A case on the grid, scenario, mean profiles and mean state of one of the reference's own restart
-    files (tests/golden/restart_fixtures.npz, extracted by tests/golden/make_restart_golden.py): the
-    (0,0) pencil is the stored mean state (collocation values -> B-spline coefficients), the other
-    pencils of an Nx x Nz wave space are synthetic perturbations."""
+    files (tests/golden/restart_fixtures.npz, extracted by tests/golden/make_restart_golden.py).  Restart
+    files hold B-SPLINE COEFFICIENTS (support::save_coefficients; the bar_* samples likewise,
+    support.cpp:655-660): the (0,0) pencil is the stored mean state as it is, the reference profiles
+    are the stored mean coefficients evaluated at the collocation points (D0 c), and the other pencils
+    of an Nx x Nz wave space are synthetic perturbations."""
     G = np.load(os.path.join(ROOT, "tests", "golden", "restart_fixtures.npz"))
     g = lambda key: G[f"{name}/{key}"]
     k, Ny = int(g("k")), int(g("Ny"))
     bop = sz.BsplineOp.from_breakpoints(k, g("breakpoints_y"))
     scenario = dict(Re=float(g("Re")), Pr=float(g("Pr")), Ma=float(g("Ma")), alpha=float(g("alpha")), gamma=float(g("gamma")))
+    D0 = bop.dense(0)
+    val = lambda c: D0 @ c                                      # coefficients -> collocation-point values
     u = g("bar_u")
-    refs = synth.reference_profiles_from_means(g("bar_rho")[0], u[0], u[1], u[2], g("bar_T")[0], g("bar_mu")[0], scenario)
-    T = g("bar_T")[0]
+    T = val(g("bar_T")[0])
+    refs = synth.reference_profiles_from_means(val(g("bar_rho")[0]), val(u[0]), val(u[1]), val(u[2]), T, val(g("bar_mu")[0]),
+                                               scenario)
     walls = dict(enforce_lower=True, enforce_upper=True, lower=(float(T[0]), 0.0, 0.0, 0.0), upper=(float(T[-1]), 0.0, 0.0, 0.0))
     wg = sz.wavegrid(Nx, Nz, float(g("Lx")), float(g("Lz")))
     km, kn, act = sz.wavenumbers(wg)
     km, kn = km[act], kn[act]
     x = 1e-2 * synth.state(km, kn, Ny, seed)
-    D0 = bop.dense(0)
     zero = np.flatnonzero((km == 0) & (kn == 0))
     assert len(zero) == 1
     for f, key in enumerate(("rho_E", "rho_u", "rho_v", "rho_w", "rho")):          # ndx::{e, mx, my, mz, rho}
-        x[zero[0], f] = np.linalg.solve(D0, g(key).real)
+        x[zero[0], f] = g(key).real
     phi = complex(-synth.delta_t(float(g("Ly"))) * synth.SMR91_BETA[0], 0.0)
     return Case("restart:" + name, bop, refs, scenario, walls, None, km, kn, x, phi, False)
 

@@ -53,22 +53,27 @@ def test_oracle_bspline_operators_match_the_references_stored_operators(name):
 
 
 def test_restart_mean_state_is_consistent_with_its_profiles():
-    """Restart files hold collocation-point VALUES (support::save_collocation_values): for these
-    one-dimensional mean states the (0,0) mode of rho is the stored mean profile itself, and the
-    B-spline coefficients follow from the mass matrix D0 (a check of the fixture extraction and of the
-    operator orientation)."""
+    """Restart files hold B-spline COEFFICIENTS (support::save_coefficients; the bar_* samples are
+    "(B-spline coefficient, tensor component, sample number)", support.cpp:655-660): for these
+    one-dimensional mean states the (0,0) mode of rho is the stored mean-density sample itself, and the
+    collocation-point values follow from the mass matrix D0 (a check of the fixture extraction and of the
+    operator orientation: density stays positive and bounded, the wall velocity vanishes)."""
     import suzerain_b200 as sz
     for name in [str(n) for n in GOLD["state_names"]]:
-        vals = gold(name, "rho")
-        assert np.abs(vals.imag).max() == 0.0
-        assert np.array_equal(vals.real, gold(name, "bar_rho")[0]), name
+        coef = gold(name, "rho")
+        assert np.abs(coef.imag).max() == 0.0
+        assert np.array_equal(coef.real, gold(name, "bar_rho")[0]), name
         bop = sz.BsplineOp.from_breakpoints(int(gold(name, "k")), gold(name, "breakpoints_y"))
         D0 = bop.dense(0)
-        coef = np.linalg.solve(D0, vals.real)
-        assert np.abs(D0 @ coef - vals.real).max() <= 1e-13 * np.abs(vals).max()
+        rho = D0 @ coef.real
+        assert rho.min() > 0.5 and rho.max() < 2.0
+        # clamped B-splines interpolate their end coefficients: wall values are the first / last coefficient
+        assert abs(rho[0] - coef.real[0]) <= 1e-14 and abs(rho[-1] - coef.real[-1]) <= 1e-14
+        u = (D0 @ gold(name, "rho_u").real) / rho
+        assert abs(u[0]) <= 1e-14 and abs(u[-1]) <= 1e-12                     # no slip
         # momentum over density is the stored mean velocity up to the sampling window (bar_* are running means)
-        u = gold(name, "rho_u").real / vals.real
-        assert np.abs(u - gold(name, "bar_u")[0]).max() <= 2e-3 * np.abs(u).max(), name
+        ubar = D0 @ gold(name, "bar_u")[0]
+        assert np.abs(u - ubar).max() <= 2e-3 * np.abs(u).max(), name
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/fields"), reason="reference tree not present")
