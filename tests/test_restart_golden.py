@@ -93,3 +93,21 @@ def test_h5lite_reads_every_reference_restart_file():
     f = H5File("/root/reference/fields/channel_k08.h5")
     assert np.array_equal(f["Dy1T"], gold("channel_k08", "Dy1T"))
     assert f.attrs("Dy1T")["kl"][0] == 6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/fields"), reason="reference tree not present")
+def test_restart_loader_on_the_bench_grid_file():
+    """suzerain_b200.restart.load on fields/channel_k08.h5 -- the bench grid and scenario."""
+    from suzerain_b200 import restart
+    r = restart.load("/root/reference/fields/channel_k08.h5")
+    assert (r.Nx, r.Ny, r.Nz, r.k, r.htdelta, r.Ly) == (1, 96, 1, 8, 3.0, 2.0)
+    assert r.scenario == dict(Re=3000.0, Pr=0.7, Ma=1.5, alpha=0.0, beta=0.7, gamma=1.4)      # = synth.SCENARIO + BETA_VISC
+    bop = r.bsplineop()
+    for d in (0, 1, 2):
+        want = r.operators[d]
+        assert np.abs(np.asarray(bop.storage[d]) - want).max() <= 5e-13 * np.abs(want).max()
+    st = r.state()
+    assert st.shape == (1, 5, 96) and np.array_equal(st[0, 4].real, gold("channel_k08", "rho").real)
+    prof = r.mean_profiles(bop)
+    assert prof["bar_rho"].shape == (1, 96) and prof["bar_u"].shape == (3, 96)
+    assert abs(prof["bar_u"][0, 0]) <= 1e-14 and 0.5 < prof["bar_rho"].min()
