@@ -59,6 +59,7 @@ class BsplineOp:
         self.max_kl = L.szb_bsplineop_max_kl(h)
         self.max_ku = L.szb_bsplineop_max_ku(h)
         self.ld = L.szb_bsplineop_ld(h)
+        self.breakpoints = None
 
     @classmethod
     def from_breakpoints(cls, k, breakpoints, nderiv=None):
@@ -69,7 +70,21 @@ class BsplineOp:
         h = C.c_void_p()
         _L.check("szb_bsplineop_alloc",
                  L.szb_bsplineop_alloc(k, len(b), b.ctypes.data_as(_L.c_double_p), nderiv, C.byref(h)))
-        return cls(h.value)
+        out = cls(h.value)
+        out.breakpoints = b.copy()
+        return out
+
+    def knots(self):
+        """The clamped knot vector: each end breakpoint with multiplicity k (what the reference stores as
+        /knots next to /breakpoints_y, support.cpp save_bsplines)."""
+        b = self.breakpoints
+        return np.concatenate([np.full(self.k - 1, b[0]), b, np.full(self.k - 1, b[-1])])
+
+    def integration_weights(self):
+        """w with  int f dy = w . coefficients  (suzerain_bspline_integration_coefficients, used by the bulk
+        constraints of treatment_constraint.cpp):  int B_j = (t_{j+k} - t_j) / k."""
+        t = self.knots()
+        return (t[self.k:] - t[:-self.k]) / self.k
 
     @classmethod
     def from_storage(cls, k, n, nderiv, kl, ku, storage):

@@ -33,6 +33,8 @@ def test_product_bspline_operators_match_the_references_stored_operators(name):
     bop = sz.BsplineOp.from_breakpoints(k, bp)
     assert (bop.n, bop.max_kl, bop.max_ku) == (Ny, int(gold(name, "kl")), int(gold(name, "ku")))
     assert np.abs(bop.greville() - gold(name, "collocation_points_y")).max() <= 4 * EPS * Ly
+    assert np.array_equal(bop.knots(), gold(name, "knots"))
+    assert np.abs(bop.integration_weights() - gold(name, "integration_weights")).max() <= 4 * EPS * Ly
     for d in range(3):
         want = gold(name, f"Dy{d}T")
         got = np.asarray(bop.storage[d])
