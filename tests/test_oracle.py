@@ -282,9 +282,10 @@ def test_shard_bounds_balance_active_pencils():
 
 
 def test_window_lu_models_match_lapack():
-    """The executable models of the two fused kernels' index algebra (tools/)."""
+    """The executable models of the fused kernels' index algebra and pipeline schedules (tools/); the
+    pipelined one also race-checks the split block update that is planned for the v4 kernel."""
     import importlib.util
-    for name in ("window_lu_model", "blocked_window_model"):
+    for name in ("window_lu_model", "blocked_window_model", "pipelined_window_model"):
         spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)

@@ -18,6 +18,13 @@ The model executes the two sides of an iteration in both orders and records ever
 array element each side reads or writes; any element written by one side and touched by
 the other within the same iteration is reported as a race.
 
+split_u0=True is a schedule that is NOT in the kernel yet (round-2 candidate, DESIGN 7.1a'): the
+update of block t+1 against pivots 0..3 of panel t ("u0a") moves behind the update warps' own work
+of the iteration, concurrent with the panel warps' last column step (multipliers and pivot slots are
+published column by column), so that the all-warps stage before F(t+1) shrinks to a rank-one update of
+block t+1 with the last pivot plus the in-place U rows of the columns past it -- which touch disjoint
+columns and need no barrier between them.  The model checks it for races and against LAPACK.
+
     python tools/pipelined_window_model.py      # self-test against SciPy LAPACK
 """
 import numpy as np
@@ -43,10 +50,15 @@ class Shared:
 
 
 class Log:
+    """Accesses per actor.  "panel" / "update" are the two sides of an iteration; with the split block
+    update the panel side is "panel" (columns 0..3) + "panel4" (last column) and the update side is
+    "update" (U, R, A) + "u0a" (block t+1 against pivots 0..3), where "u0a" is ordered after "panel" by a
+    flag and runs concurrently with "panel4"."""
+
     def __init__(self):
         self.actor = None
-        self.r = {"panel": set(), "update": set()}
-        self.w = {"panel": set(), "update": set()}
+        self.r = {k: set() for k in ("panel", "panel4", "update", "u0a")}
+        self.w = {k: set() for k in ("panel", "panel4", "update", "u0a")}
 
     def read(self, name, idx):
         if self.actor:
@@ -57,14 +69,17 @@ class Log:
             self.w[self.actor].add((name, idx))
 
     def check_and_reset(self, where):
-        bad = (self.w["panel"] & (self.r["update"] | self.w["update"])) | (self.w["update"] & self.r["panel"])
+        def conflict(a, b):
+            return (self.w[a] & (self.r[b] | self.w[b])) | (self.w[b] & self.r[a])
+        # concurrent pairs: panel (all of it) vs update main; the last panel column vs the early block update
+        bad = conflict("panel", "update") | conflict("panel4", "update") | conflict("panel4", "u0a")
         assert not bad, f"race at {where}: {sorted(bad)[:6]}"
         for d in (self.r, self.w):
             for k in d:
                 d[k].clear()
 
 
-def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
+def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first", split_u0=False):
     assert N % P == 0 and (KL + 1) % P == 0
     KV = KL + KU
     RW = KL + P + 1                 # matrix row slots; slot RW = RHS
@@ -108,7 +123,7 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
     ipiv = np.zeros(N, dtype=np.int32)
     info = [0]
 
-    def panel_side(t):
+    def panel_side(t, early_u0=None):
         nonlocal ju
         j, par = P * t, t & 1
         log.actor = "panel"
@@ -124,6 +139,10 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
                     a[s_, m] = W[s_, (j + m) % CW]
         # ---- F(t) ----
         for k in range(P):
+            if split_u0 and k == P - 1:
+                if early_u0 is not None:
+                    early_u0()                       # order "u0a before the last column" (it is concurrent)
+                log.actor = "panel4"
             col = j + k
             hi = min(col + KL, N - 1)
             best, bl, bs = -1.0, None, None
@@ -156,10 +175,10 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
                     L[col, lg[s] - (col + 1)] = l
                 for m in range(k + 1, P):
                     a[s, m] -= l * piv[m]
+            # multipliers of this column by slot, published column by column (zeros for pivot rows)
+            for s in range(NS):
+                lp[par, s, k] = a[s, k] if pk[s] == P else 0.0
         for s in range(NS):
-            for m in range(P):
-                v = a[s, m] if m < pk[s] else 0.0
-                lp[par, s, m] = v
             isp[par, s] = pk[s] < P
         juv[par] = ju
         log.actor = None
@@ -171,6 +190,24 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
             jo = j - P
             ops = [pivslot[par ^ 1, k] for k in range(P)]
             c_lo, c_hi = (jo + P, jo + 2 * P - 1) if lookahead else (jo + 2 * P, N)
+            if lookahead and split_u0:
+                # block t already carries pivots 0..P-2 of panel t-1 (u0a): only the last pivot is left, and
+                # its row needs no fix-up.  Concurrently: X for the columns past block t.
+                for c in range(jo + P, min(jo + 2 * P - 1, N - 1) + 1):
+                    cs = c % CW
+                    u4 = W[ops[P - 1], cs]
+                    for s in range(NS):
+                        if isp[par ^ 1, s]:
+                            continue
+                        W[s, cs] = W[s, cs] - lp[par ^ 1, s, P - 1] * u4
+                for c in range(jo + 2 * P, juv[par ^ 1] + 1):
+                    cs = c % CW
+                    u = [W[ops[m], cs] for m in range(P)]
+                    for k in range(1, P):
+                        for m in range(k):
+                            u[k] -= lp[par ^ 1, ops[k], m] * u[m]
+                        W[ops[k], cs] = u[k]
+                return
             if lookahead:
                 # ---- phase 1: the pivot rows of panel t-1 become rows of U, in place, for every
                 # trailing column (one thread per column) ----
@@ -211,9 +248,41 @@ def pipelined_solve_T(N, KL, KU, entry, b, P=5, order="panel-first"):
         assemble_rows((j + RW) // P, par)
         log.actor = None
 
+    def early_block_update(t):
+        """u0a: block t+1 against pivots 0..P-2 of panel t, as soon as the panel warps have published them
+        (every thread redoes the small triangular fix-up of the pivot rows for its column)."""
+        j, par = P * t, t & 1
+        log.actor = "u0a"
+        ops = [pivslot[par, k] for k in range(P - 1)]
+        for c in range(j + P, min(j + 2 * P - 1, N - 1) + 1):
+            cs = c % CW
+            u = [W[ops[m], cs] for m in range(P - 1)]
+            for k in range(1, P - 1):
+                for m in range(k):
+                    u[k] -= lp[par, ops[k], m] * u[m]
+            for s in range(NS):
+                if s in ops:
+                    continue
+                w = W[s, cs]
+                for m in range(P - 1):
+                    w -= lp[par, s, m] * u[m]
+                W[s, cs] = w
+        log.actor = "panel"
+
     for t in range(N // P):
         update_side(t, True)                      # U0(t-1), then the panel warp is released
-        if order == "panel-first":
+        if split_u0:
+            # the update side's main work must precede its early block update (same warps); the early
+            # update waits for the flag "columns 0..P-2 published"
+            if order == "panel-first":
+                done = []
+                def hook():
+                    update_side(t, False); early_block_update(t); done.append(1)
+                panel_side(t, early_u0=hook)
+            else:
+                update_side(t, False)
+                panel_side(t, early_u0=lambda: early_block_update(t))
+        elif order == "panel-first":
             panel_side(t); update_side(t, False)
         else:
             update_side(t, False); panel_side(t)
@@ -248,17 +317,17 @@ def _selftest():
                 ab[KL + KU + i - c, c] = A[i, c]
         lu, piv, info = lapack.zgbtrf(ab, KL, KU)
         xr, _ = lapack.zgbtrs(lu, KL, KU, b, piv, trans=1)
-        for order in ("panel-first", "update-first"):
-            x, ipiv, L, info3 = pipelined_solve_T(N, KL, KU, lambda i, c: A[i, c], b, order=order)
+        for order, split in (("panel-first", False), ("update-first", False), ("panel-first", True), ("update-first", True)):
+            x, ipiv, L, info3 = pipelined_solve_T(N, KL, KU, lambda i, c: A[i, c], b, order=order, split_u0=split)
             assert info3 == 0
             assert np.array_equal(ipiv - 1, piv), (N, KL, KU)
             err = np.abs(x - xr).max() / np.abs(xr).max()
             kv = KL + KU
             Lref = np.array([[lu[kv + i, jj] if jj + i < N else 0 for i in range(1, KL + 1)] for jj in range(N)])
             lerr = np.abs(L - Lref).max()
-            assert err < 1e-9 and lerr < 1e-9, (N, KL, KU, order, err, lerr)
+            assert err < 1e-9 and lerr < 1e-9, (N, KL, KU, order, split, err, lerr)
         print(f"N={N} KL={KL} KU={KU}: pivots identical ({(piv != np.arange(N)).sum()} non-trivial), "
-              f"x relerr {err:.2e}, L abs err {lerr:.2e}, no races in either order")
+              f"x relerr {err:.2e}, L abs err {lerr:.2e}, no races in either order, with and without the split block update")
 
 
 if __name__ == "__main__":
