@@ -37,6 +37,9 @@
 
 #include "invert_common.cuh"
 
+// SZB_PIPE_SPLITU0 (make SPLITU0=1): the split block update of DESIGN 7.1a' -- correct (all GPU tests, identical
+// pivots) but measured slower (23.1 vs 21.9 ms), so it is off by default.
+
 // Optional phase timing (make PROF=1): per-phase clock64() deltas of the panel warp and of
 // update warp 0, summed over all pencils and CTAs; read back with szb_debug_pipe_prof().
 #ifdef SZB_PIPE_PROF
@@ -329,6 +332,41 @@ __device__ __forceinline__ void lookahead_phases(const SM &S, unsigned sbase, in
 #pragma unroll
     for (int m = 0; m < P; ++m) ps[m] = opiv[m];
     const int wtot = S.misc[2 + (par ^ 1)] - j + 1;               // columns j .. ju(t-1)
+#ifdef SZB_PIPE_SPLITU0
+    // Block t already carries pivots 0..3 of panel t-1 (early_block_update during F(t-1)'s last column):
+    // what is left is a rank-one update of block t with the last pivot row, which needs no fix-up, and the
+    // in-place U rows of the columns past block t.  Disjoint columns: one barrier.
+    {
+        const unsigned long long omask = (unsigned) S.misc[6 + 2 * (par ^ 1)]
+            | (unsigned long long) (unsigned) S.misc[7 + 2 * (par ^ 1)] << 32;
+        constexpr int XT0 = ((NS * P + 31) / 32) * 32;             // first thread of the X' part (a warp boundary)
+        static_assert(XT0 < NT, "threads left for the trailing columns");
+        if (tid < XT0) {
+            for (int e = tid; e < NS * P; e += XT0) {
+                const int s = e / P, m = e - s * P;
+                int ccs = jc + m; if (ccs >= CW) ccs -= CW;
+                cplx w = S.win[(size_t) s * CW + ccs];
+                submul(w, lpo[s * P + P - 1], S.win[(size_t) ps[P - 1] * CW + ccs]);
+                sts_if(sbase + (unsigned) PipeLayout<W>::win + 16u * (unsigned) (s * CW + ccs), w, !((omask >> s) & 1));
+            }
+        } else {
+            for (int c = P + tid - XT0; c < wtot; c += NT - XT0) {
+                int ccs = jc + c; if (ccs >= CW) ccs -= CW;
+                cplx u[P];
+#pragma unroll
+                for (int k = 0; k < P; ++k) u[k] = S.win[(size_t) ps[k] * CW + ccs];
+#pragma unroll
+                for (int k = 1; k < P; ++k) {
+#pragma unroll
+                    for (int i = 0; i < k; ++i) submul(u[k], lpo[ps[k] * P + i], u[i]);
+                    S.win[(size_t) ps[k] * CW + ccs] = u[k];
+                }
+            }
+        }
+        bar_sync_n<1>(NT);
+        return;
+    }
+#endif
     for (int c = tid; c < wtot; c += NT) {
         int ccs = jc + c; if (ccs >= CW) ccs -= CW;
         cplx u[P];
@@ -374,6 +412,8 @@ invert_pipe_kernel(const PipeArgs A)
     pin(sbase);
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
     constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_PP = 7;
+    constexpr int BAR_C3 = 8;           // SZB_PIPE_SPLITU0: panel warps arrive once columns 0..3 are published
+    (void) BAR_C3;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
 
@@ -627,6 +667,9 @@ invert_pipe_kernel(const PipeArgs A)
                 // steps next to the pivot search of the following one.
                 double rd_d = fma(a[0].x, a[0].x, a[0].y * a[0].y), rd_r = rcp_seed(rd_d);
                 double rd_e = fma(-rd_d, rd_r, 1.0);
+#ifdef SZB_PIPE_SPLITU0
+                int c3 = 0;
+#endif
 #pragma unroll 1
                 for (int k = 0; k < P; ++k) {
                     const int col = j + k, hi = col + KL;
@@ -736,8 +779,14 @@ invert_pipe_kernel(const PipeArgs A)
                         rd_r = rcp_seed(rd_d);
                         rd_e = fma(-rd_d, rd_r, 1.0);
                     }
+#ifdef SZB_PIPE_SPLITU0
+                    if (k == P - 2) { bar_arrive_n<BAR_C3>(NTU + 32 * W::NWP); c3 = 1; }
+#endif
                     Lcol += KL - 1;
                 }
+#ifdef SZB_PIPE_SPLITU0
+                if (!c3) bar_arrive_n<BAR_C3>(NTU + 32 * W::NWP);        // a zero pivot cut the panel short
+#endif
                 PROF_MARK(2);
                 {
                     const unsigned m = __ballot_sync(0xffffffffu, pk >= 0 && pk < P);
@@ -840,6 +889,33 @@ invert_pipe_kernel(const PipeArgs A)
                     }
                     PROF_MARK(3);
                 }
+#ifdef SZB_PIPE_SPLITU0
+                // ---- U0a(t): block t+1 against pivots 0..3 of THIS panel, as soon as the panel warps have
+                // published them (they are in their last column step meanwhile).  Every thread redoes the
+                // small unit-lower-triangular fix-up of the four pivot rows for its column. ----
+                bar_sync_n<BAR_C3>(NTU + 32 * W::NWP);
+                {
+                    const int *npiv = S.pivslot + par * P;
+                    const cplx *lpn = S.lp + (size_t) par * NS * P;
+                    int q0 = npiv[0], q1 = npiv[1], q2 = npiv[2], q3 = npiv[3];
+                    for (int e = tid; e < NS * P; e += NTU) {
+                        const int s = e / P, m = e - s * P;
+                        int ccs = jc + P + m; if (ccs >= CW) ccs -= CW;
+                        const cplx u0 = S.win[(size_t) q0 * CW + ccs];
+                        cplx u1 = S.win[(size_t) q1 * CW + ccs]; submul(u1, lpn[q1 * P], u0);
+                        cplx u2 = S.win[(size_t) q2 * CW + ccs]; submul(u2, lpn[q2 * P], u0); submul(u2, lpn[q2 * P + 1], u1);
+                        cplx u3 = S.win[(size_t) q3 * CW + ccs]; submul(u3, lpn[q3 * P], u0); submul(u3, lpn[q3 * P + 1], u1);
+                        submul(u3, lpn[q3 * P + 2], u2);
+                        cplx w = S.win[(size_t) s * CW + ccs];
+                        submul(w, lpn[s * P], u0); submul(w, lpn[s * P + 1], u1);
+                        submul(w, lpn[s * P + 2], u2); submul(w, lpn[s * P + 3], u3);
+                        // all of a column's readers of the pivot rows are ahead of its writers: rows q0..q3 are
+                        // never written here
+                        sts_if(sbase + (unsigned) Y::win + 16u * (unsigned) (s * CW + ccs), w,
+                               s != q0 && s != q1 && s != q2 && s != q3);
+                    }
+                }
+#endif
                 bar_sync_n<BAR_ALL>(NT);
                 PROF_MARK(5);
                 info = S.misc[4 + buf];
