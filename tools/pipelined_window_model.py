@@ -18,7 +18,8 @@ The model executes the two sides of an iteration in both orders and records ever
 array element each side reads or writes; any element written by one side and touched by
 the other within the same iteration is reported as a race.
 
-split_u0=True is a schedule that is NOT in the kernel yet (round-2 candidate, DESIGN 7.1a'): the
+split_u0=True is the schedule the kernel runs when built with `make SPLITU0=1` (DESIGN 7.1a'; correct but
+measured slower, so off by default): the
 update of block t+1 against pivots 0..3 of panel t ("u0a") moves behind the update warps' own work
 of the iteration, concurrent with the panel warps' last column step (multipliers and pivot slots are
 published column by column), so that the all-warps stage before F(t+1) shrinks to a rank-one update of
