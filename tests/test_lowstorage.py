@@ -149,3 +149,37 @@ def test_gpu_steps_track_the_oracle_through_the_same_driver():
     assert int(H.info.abs().max()) == 0
     assert np.all(got[~act] == 0)
     assert pc.relmax(got[act], ao.data) <= 1e-11
+
+
+def test_step_honours_max_delta_t_and_propagates_nan():
+    """math::minnan semantics of lowstorage::step (lowstorage.hpp:1495-1499) with do-nothing operators."""
+    class L0:
+        def __init__(self):
+            self.phis = []
+
+        def apply_mass_plus_scaled_operator(self, phi, state):
+            self.phis.append(("apply", phi))
+
+        def accumulate_mass_plus_scaled_operator(self, phi, input, beta, output):
+            self.phis.append(("accumulate", phi, beta))
+
+        def invert_mass_plus_scaled_operator(self, phi, state):
+            self.phis.append(("invert", phi))
+
+    class N0:
+        def __init__(self, cands):
+            self.cands = cands
+
+        def apply_operator(self, time, state, method, substep_index):
+            return self.cands
+
+    m = ls.SMR91
+    a, b = ls.State(np.ones(3)), ls.State(np.zeros(3))
+    L = L0()
+    dt = ls.step(m, ls.delta_t_reducer, L, 0.5, N0([0.4, 0.2]), 0.0, a, b, max_delta_t=0.05)
+    assert dt == 0.05
+    assert L.phis[0] == ("apply", 0.05 * m.alpha(0)) and L.phis[1] == ("invert", -0.05 * m.beta(0))
+    assert L.phis[2] == ("accumulate", 0.05 * m.alpha(1), 0.5 * 0.05 * m.zeta(1))
+    assert L.phis[-1] == ("invert", -0.05 * m.beta(2))
+    assert ls.step(m, ls.delta_t_reducer, L0(), 0.5, N0([0.4, 0.2]), 0.0, a, b) == 0.2
+    assert np.isnan(ls.step(m, ls.delta_t_reducer, L0(), 0.5, N0([float("nan"), 0.2]), 0.0, a, b, max_delta_t=0.05))
