@@ -310,6 +310,32 @@ __device__ __noinline__ double2 exact_recip(double x, double y)
     return make_double2(r.x, r.y);
 }
 
+// SZB_PIPE_SPLITU0 -- U0a(t): block t+1 against pivots 0..3 of panel t, once the panel warps have published
+// them (they are in their last column step meanwhile).  Every thread redoes the small unit-lower-triangular
+// fix-up of the four pivot rows for its column; rows q0..q3 are read only.  jc: column slot of block t.
+template <class W, class SM>
+__device__ __forceinline__ void early_block_update(const SM &S, unsigned sbase, int jc, int par, int t0, int nt)
+{
+    constexpr int NS = W::NS, CW = W::CW;
+    const int *npiv = S.pivslot + par * P;
+    const cplx *lpn = S.lp + (size_t) par * NS * P;
+    const int q0 = npiv[0], q1 = npiv[1], q2 = npiv[2], q3 = npiv[3];
+    for (int e = t0; e < NS * P; e += nt) {
+        const int s = e / P, m = e - s * P;
+        int ccs = jc + P + m; if (ccs >= CW) ccs -= CW;
+        const cplx u0 = S.win[(size_t) q0 * CW + ccs];
+        cplx u1 = S.win[(size_t) q1 * CW + ccs]; submul(u1, lpn[q1 * P], u0);
+        cplx u2 = S.win[(size_t) q2 * CW + ccs]; submul(u2, lpn[q2 * P], u0); submul(u2, lpn[q2 * P + 1], u1);
+        cplx u3 = S.win[(size_t) q3 * CW + ccs]; submul(u3, lpn[q3 * P], u0); submul(u3, lpn[q3 * P + 1], u1);
+        submul(u3, lpn[q3 * P + 2], u2);
+        cplx w = S.win[(size_t) s * CW + ccs];
+        submul(w, lpn[s * P], u0); submul(w, lpn[s * P + 1], u1);
+        submul(w, lpn[s * P + 2], u2); submul(w, lpn[s * P + 3], u3);
+        sts_if(sbase + (unsigned) PipeLayout<W>::win + 16u * (unsigned) (s * CW + ccs), w,
+               s != q0 && s != q1 && s != q2 && s != q3);
+    }
+}
+
 // Start of iteration t > 0, all compute warps (the panel warp has nothing else to do until
 // block t is final):
 //   X(t-1)   the five pivot rows of panel t-1 become rows of U, in place, for every trailing
@@ -413,7 +439,12 @@ invert_pipe_kernel(const PipeArgs A)
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
     constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_PP = 7;
     constexpr int BAR_C3 = 8;           // SZB_PIPE_SPLITU0: panel warps arrive once columns 0..3 are published
-    (void) BAR_C3;
+#if defined(SZB_PIPE_SPLITU0) && SZB_PIPE_SPLITU0 == 2
+    constexpr int C3N = NTU + W::NTA + 32 * W::NWP;
+#else
+    constexpr int C3N = NTU + 32 * W::NWP;
+#endif
+    (void) BAR_C3; (void) C3N;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
 
@@ -780,12 +811,12 @@ invert_pipe_kernel(const PipeArgs A)
                         rd_e = fma(-rd_d, rd_r, 1.0);
                     }
 #ifdef SZB_PIPE_SPLITU0
-                    if (k == P - 2) { bar_arrive_n<BAR_C3>(NTU + 32 * W::NWP); c3 = 1; }
+                    if (k == P - 2) { bar_arrive_n<BAR_C3>(C3N); c3 = 1; }
 #endif
                     Lcol += KL - 1;
                 }
 #ifdef SZB_PIPE_SPLITU0
-                if (!c3) bar_arrive_n<BAR_C3>(NTU + 32 * W::NWP);        // a zero pivot cut the panel short
+                if (!c3) bar_arrive_n<BAR_C3>(C3N);        // a zero pivot cut the panel short
 #endif
                 PROF_MARK(2);
                 {
@@ -893,28 +924,14 @@ invert_pipe_kernel(const PipeArgs A)
                 // ---- U0a(t): block t+1 against pivots 0..3 of THIS panel, as soon as the panel warps have
                 // published them (they are in their last column step meanwhile).  Every thread redoes the
                 // small unit-lower-triangular fix-up of the four pivot rows for its column. ----
-                bar_sync_n<BAR_C3>(NTU + 32 * W::NWP);
-                {
-                    const int *npiv = S.pivslot + par * P;
-                    const cplx *lpn = S.lp + (size_t) par * NS * P;
-                    int q0 = npiv[0], q1 = npiv[1], q2 = npiv[2], q3 = npiv[3];
-                    for (int e = tid; e < NS * P; e += NTU) {
-                        const int s = e / P, m = e - s * P;
-                        int ccs = jc + P + m; if (ccs >= CW) ccs -= CW;
-                        const cplx u0 = S.win[(size_t) q0 * CW + ccs];
-                        cplx u1 = S.win[(size_t) q1 * CW + ccs]; submul(u1, lpn[q1 * P], u0);
-                        cplx u2 = S.win[(size_t) q2 * CW + ccs]; submul(u2, lpn[q2 * P], u0); submul(u2, lpn[q2 * P + 1], u1);
-                        cplx u3 = S.win[(size_t) q3 * CW + ccs]; submul(u3, lpn[q3 * P], u0); submul(u3, lpn[q3 * P + 1], u1);
-                        submul(u3, lpn[q3 * P + 2], u2);
-                        cplx w = S.win[(size_t) s * CW + ccs];
-                        submul(w, lpn[s * P], u0); submul(w, lpn[s * P + 1], u1);
-                        submul(w, lpn[s * P + 2], u2); submul(w, lpn[s * P + 3], u3);
-                        // all of a column's readers of the pivot rows are ahead of its writers: rows q0..q3 are
-                        // never written here
-                        sts_if(sbase + (unsigned) Y::win + 16u * (unsigned) (s * CW + ccs), w,
-                               s != q0 && s != q1 && s != q2 && s != q3);
-                    }
-                }
+#if SZB_PIPE_SPLITU0 == 2
+                // variant 2 (UNTESTED, for round 2): the assembly warps, which idle after A(t), take the early
+                // update; the update warps only announce that R(t-1) is done
+                bar_arrive_n<BAR_C3>(C3N);
+#else
+                bar_sync_n<BAR_C3>(C3N);
+                early_block_update<W>(S, sbase, jc, par, tid, NTU);
+#endif
 #endif
                 bar_sync_n<BAR_ALL>(NT);
                 PROF_MARK(5);
@@ -941,6 +958,10 @@ invert_pipe_kernel(const PipeArgs A)
                     assemble_block<W>(K, S, DStaged(K, S.drow + par * 3 * W::LDMAX, yI), km, kn, yI, dst, ta, W::NTA);
 #endif
                 stage_rowblock<W>(K, S, yI + 1, par ^ 1, ta, W::NTA);
+#if defined(SZB_PIPE_SPLITU0) && SZB_PIPE_SPLITU0 == 2
+                bar_sync_n<BAR_C3>(C3N);
+                early_block_update<W>(S, sbase, jc, par, ta, W::NTA);
+#endif
                 bar_sync_n<BAR_ALL>(NT);
                 info = S.misc[4 + buf];
                 if (info) break;
