@@ -584,6 +584,31 @@ static size_t invert_slot_bytes(const szb_imexop *op, int method)
     return (b + 255) & ~(size_t) 255;
 }
 
+}  // extern "C"
+
+namespace szb {
+int invert_fused_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                          const double *d_km, const double *d_kn, const int *d_index,
+                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                          int *d_iters, cudaStream_t stream, int zero_wall_rhs)
+{
+    static const int which = [] {
+        const char *e = std::getenv("SZB_INVERT");
+        return (e && e[0] == 'v' && e[1] == '4') ? 4 : 5;
+    }();
+    int rc = 1;
+    if (which == 5)
+        rc = invert_sync_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info, d_iters,
+                                  stream, zero_wall_rhs);
+    if (rc == 1)
+        rc = invert_pipe_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info, d_iters,
+                                  stream, zero_wall_rhs);
+    return rc;
+}
+}  // namespace szb
+
+extern "C" {
+
 size_t szb_imexop_workspace_bytes(const szb_imexop *op) { return op ? op->work_bytes : 0; }
 
 int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
@@ -629,29 +654,17 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
         d_km = d_kn = op->d_zero;
     }
 
-    // zgbsv with a single right hand side per pencil: the pipelined blocked
-    // shared-memory-window kernel (invert_pipe.cu).  SZB_INVERT=v1 / v2 / v3 in the
-    // environment selects the generic global-memory kernel / the register-window kernel
-    // (invert_window.cu) / the unpipelined blocked kernel (invert_blocked.cu).
+    // zgbsv with a single right hand side per pencil: the fused shared-memory-window kernels
+    // (invert_sync.cu: v5, default; invert_pipe.cu: v4 with SZB_INVERT=v4 or when v5 has no
+    // instantiation).  SZB_INVERT=v1 selects the generic global-memory kernel below.
     if (spec->method == SZB_SOLVER_ZGBSV && nextra == 0) {
-        static const int which = [] {
-            const char *e = std::getenv("SZB_INVERT");
-            return (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '4') ? e[1] - '0' : 4;
-        }();
-        int rc = 1;
-        if (which == 4)
-            rc = invert_pipe_dispatch(op, phi, npencil, d_km, d_kn, d_index,
-                                      reinterpret_cast<cplx *>(d_state), field_stride,
-                                      pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
-        if (which == 3 || (which == 4 && rc == 1))
-            rc = invert_blocked_dispatch(op, phi, npencil, d_km, d_kn, d_index,
-                                         reinterpret_cast<cplx *>(d_state), field_stride,
-                                         pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
-        else if (which == 2)
-            rc = invert_window_dispatch(op, phi, npencil, d_km, d_kn, d_index,
-                                        reinterpret_cast<cplx *>(d_state), field_stride,
-                                        pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
-        if (rc <= 0) return rc;
+        static const bool generic = [] { const char *e = std::getenv("SZB_INVERT"); return e && e[0] == 'v' && e[1] == '1'; }();
+        if (!generic) {
+            const int rc = invert_fused_dispatch(op, phi, npencil, d_km, d_kn, d_index,
+                                                 reinterpret_cast<cplx *>(d_state), field_stride,
+                                                 pencil_stride, d_ipiv, d_info, d_iters, (cudaStream_t) stream);
+            if (rc <= 0) return rc;
+        }
     }
     // zcgbsvx with its default eps tolerance: refinement around the fused kernel (the factors
     // are recomputed per step instead of being stored); SZB_INVERT=v1 keeps the generic kernel

@@ -81,7 +81,9 @@ struct DStaged {
 template <class W>
 __device__ __forceinline__ int coef_index(int y, int sJ, int sI, int d)
 {
-    return ((d * 5 + sI) * W::CR + (y & (W::CR - 1))) * 5 + sJ;
+    // the ring holds CR consecutive collocation points (a power of two in v3 / v4, 2 kb + 1 in v5)
+    const int slot = (W::CR & (W::CR - 1)) == 0 ? (y & (W::CR - 1)) : y % W::CR;
+    return ((d * 5 + sI) * W::CR + slot) * 5 + sJ;
 }
 
 // ---- assembled entries of P (M + phi L)^T P^T from the coefficient ring ----

@@ -35,7 +35,7 @@
 #include <cstdlib>
 #include <cstdio>
 
-#include "invert_common.cuh"
+#include "invert_fused.cuh"
 
 // SZB_PIPE_SPLITU0 (make SPLITU0=1): the split block update of DESIGN 7.1a' -- correct (all GPU tests, identical
 // pivots) but measured slower (23.1 vs 21.9 ms), so it is off by default.
@@ -92,16 +92,6 @@ struct PipeCfg {
     static_assert(RW % P == 0, "window rows come in groups of five");
     static_assert(NS <= 64, "at most two panel warps");
     static_assert((CR & (CR - 1)) == 0, "ring size must be a power of two");
-};
-
-struct PipeArgs {
-    PackArgs pk;
-    int npencil; const int *index;
-    cplx *state; size_t fs, ps;
-    int *ipiv_out, *info_out, *iters_out;
-    cplx *lwork;            // per CTA: 2 buffers of N*KL multipliers
-    cplx *vwork;            // per CTA: 2 buffers of N (b -> y -> x) when they do not fit in shared memory
-    int zero_wall_rhs;      // zero the wall rows of the right hand side (not for refinement residuals)
 };
 
 template <class W>
@@ -180,89 +170,6 @@ __device__ __forceinline__ PSmem<W> pipe_carve(unsigned char *raw, int N, bool v
     return S;
 }
 
-__device__ __forceinline__ cplx shfl_c(cplx v, int src)
-{
-    return cplx(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-}
-
-// predicated stores: one instruction, no divergent branch on the panel warp's chain
-__device__ __forceinline__ void st_global_if(cplx *p, cplx v, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}"
-                 :: "l"(p), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
-}
-__device__ __forceinline__ void st_shared_if(cplx *p, cplx v, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}"
-                 :: "r"(smem_u32(p)), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
-}
-
-__device__ __forceinline__ void sts_if(unsigned sa, cplx v, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}"
-                 :: "r"(sa), "d"(v.x), "d"(v.y), "r"((int) pred) : "memory");
-}
-__device__ __forceinline__ void sts2_if(unsigned sa, int x, int y, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}"
-                 :: "r"(sa), "r"(x), "r"(y), "r"((int) pred) : "memory");
-}
-__device__ __forceinline__ void sts32_if(unsigned sa, int x, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b32 [%0], %1;\n\t}"
-                 :: "r"(sa), "r"(x), "r"((int) pred) : "memory");
-}
-__device__ __forceinline__ void sts8_if(unsigned sa, int x, bool pred)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.b8 [%0], %1;\n\t}"
-                 :: "r"(sa), "r"(x), "r"((int) pred) : "memory");
-}
-
-__device__ __forceinline__ cplx lds_c(unsigned sa)
-{
-    cplx v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sa) : "memory");
-    return v;
-}
-__device__ __forceinline__ int2 lds_i2(unsigned sa)
-{
-    int2 v;
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sa) : "memory");
-    return v;
-}
-// b / y / x vectors: shared memory, or (VG) global memory read at L2 so that values written by
-// other warps of the CTA are seen
-template <bool VG>
-__device__ __forceinline__ cplx ldv(const cplx *p)
-{
-    if (VG) { const double2 t = __ldcg(reinterpret_cast<const double2 *>(p)); return cplx(t.x, t.y); }
-    return *p;
-}
-// keep a value in a register instead of letting the compiler recompute it (S2R / LDC chains)
-// inside the panel warp's column loop
-__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
-__device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
-
-// 1/d for d in the normal range, without the special-case branch of the compiler's
-// division: the same MUFU.RCP64H seed and Newton steps as its fast path, so that the
-// panel column step stays one basic block.
-__device__ __forceinline__ double rcp_seed(double d)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    return r;
-}
-__device__ __forceinline__ double rcp_nr(double d)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    e = fma(e, e, e);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    return fma(r, e, r);
-}
-
 // Operator rows of row block yI and the reference-profile column of its new coefficient
 // point yI + 1 + ku, into the shared-memory buffers of parity `par`.
 template <class W, class SM>
@@ -278,36 +185,6 @@ __device__ __forceinline__ void stage_rowblock(const PackArgs &K, const SM &S, i
             S.refcol[par * 32 + q] = yc < K.n ? __ldg(K.refs + (size_t) q * K.n + yc) : 0.0;
         }
     }
-}
-
-// The rare exact pivot decision (near ties on the top word, two candidates in one lane,
-// tiny or huge magnitudes, zero pivots): izamax's first maximum of the full 64-bit
-// |re|+|im| with the smallest logical row breaking ties.  Returns
-// src | wq << 8 | zero-pivot << 16 | (this lane's own better slot) << 24.
-__device__ __noinline__ int exact_pivot(long long key0, long long key1, int lg0, int lg1)
-{
-    const bool sq = key1 > key0 || (key1 == key0 && key0 >= 0 && lg1 < lg0);
-    const long long kb = sq ? key1 : key0;
-    const int lgb = sq ? lg1 : lg0;
-    const int hi32 = (int) (kb >> 32);
-    const int mh = __reduce_max_sync(0xffffffffu, hi32);
-    bool iswin = hi32 == mh && kb >= 0;
-    const unsigned lo32 = (unsigned) (kb & 0xffffffffll);
-    const unsigned ml = __reduce_max_sync(0xffffffffu, iswin ? lo32 : 0u);
-    iswin = iswin && lo32 == ml;
-    const int lmin = __reduce_min_sync(0xffffffffu, iswin ? lgb : INT_MAX);
-    iswin = iswin && lgb == lmin;
-    const unsigned bal = __ballot_sync(0xffffffffu, iswin);
-    const int src = bal ? __ffs(bal) - 1 : 0;
-    const int wq = __shfl_sync(0xffffffffu, (int) sq, src);
-    const int zp = bal == 0 || __shfl_sync(0xffffffffu, (int) (kb == 0), src) != 0;
-    return src | wq << 8 | zp << 16 | (int) sq << 24;
-}
-// ... and a reciprocal that cannot overflow prematurely
-__device__ __noinline__ double2 exact_recip(double x, double y)
-{
-    const cplx r = recip_fast(cplx(x, y));
-    return make_double2(r.x, r.y);
 }
 
 // SZB_PIPE_SPLITU0 -- U0a(t): block t+1 against pivots 0..3 of panel t, once the panel warps have published
@@ -437,7 +314,7 @@ invert_pipe_kernel(const PipeArgs A)
     unsigned sbase = smem_u32(smem_raw);                          // shared-window address of the block
     pin(sbase);
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
-    constexpr int BAR_ALL = 1, BAR_FULL0 = 2, BAR_FULL1 = 3, BAR_EMPTY0 = 4, BAR_EMPTY1 = 5, BAR_UPD = 6, BAR_PP = 7;
+    constexpr int BAR_ALL = 1, BAR_UPD = 6, BAR_PP = 7;
     constexpr int BAR_C3 = 8;           // SZB_PIPE_SPLITU0: panel warps arrive once columns 0..3 are published
 #if defined(SZB_PIPE_SPLITU0) && SZB_PIPE_SPLITU0 == 2
     constexpr int C3N = NTU + W::NTA + 32 * W::NWP;
@@ -459,151 +336,7 @@ invert_pipe_kernel(const PipeArgs A)
     if (tid >= NT) {
         // =================== solver warp: L^T back substitution ===================
         const int lane = tid - NT;
-        int q = 0;
-        unsigned chunk_base = 0;        // running chunk count: ring slot and mbarrier phase
-        for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
-            const int buf = q & 1;
-            if (buf == 0) bar_sync_n<BAR_FULL0>(W::NTH); else bar_sync_n<BAR_FULL1>(W::NTH);
-            cplx *x = vbase + (size_t) buf * N;
-            const unsigned char *jpv = S.ipiv + (size_t) buf * N;
-            const cplx *Lg = lwork + (size_t) buf * lstride;
-            const int info = S.misc[buf];
-            if (info == 0) {
-                // multipliers stream in through a ring of TMA bulk copies, last columns first
-                constexpr int CH = W::CH, NB = W::NB;
-                // chunk c covers columns [CH (nchunk-1-c), +CH): aligned so that a consumed chunk is a
-                // whole number of 128-byte lines
-                const int ncols = N - 1, nchunk = (ncols + CH - 1) / CH;
-                asm volatile("fence.proxy.async;" ::: "memory");
-                auto issue = [&](int c) {
-                    const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
-                    const unsigned bytes = (unsigned) ((jhi - jlo + 1) * KL * sizeof(cplx));
-                    const unsigned slot = (chunk_base + c) % NB;
-                    mbar_expect_tx(S.mbar + slot, bytes);
-                    tma_bulk_g2s(S.lring + (size_t) slot * CH * KL, Lg + (size_t) jlo * KL, bytes,
-                                 S.mbar + slot);
-                };
-                if (lane == 0) for (int c = 0; c < min(NB, nchunk); ++c) issue(c);
-                for (int c = 0; c < nchunk; ++c) {
-                    const unsigned g = chunk_base + c, slot = g % NB, parity = (g / NB) & 1;
-                    mbar_wait(S.mbar + slot, parity);
-                    const int jlo = CH * (nchunk - 1 - c), jhi = min(jlo + CH - 1, N - 2);
-                    const cplx *Lc = S.lring + (size_t) slot * CH * KL;
-                    // Four columns at a time when none of them carries an interchange: the parts of
-                    // their four dot products that involve already final x (rows past the chunk) are
-                    // formed together and reduced with one packed butterfly (8 doubles -> 4 -> 2 -> 1
-                    // per lane), then lane 0 finishes the 4 x 4 triangle.  Otherwise column by column.
-                    bool plain = CH == 4 && jhi - jlo + 1 == CH;
-                    if (plain)
-                        plain = (jpv[jlo] | jpv[jlo + 1] | jpv[jlo + 2] | jpv[jlo + 3]) == 0;
-                    if (plain) {
-                        double v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = 0.0;
-                        for (int t = lane; t < KL; t += 32) {
-                            const int pz = jhi + 1 + t;
-                            if (pz <= N - 1) {
-                                const cplx xv = ldv<VG>(x + pz);
-#pragma unroll
-                                for (int qq = 0; qq < 4; ++qq) {
-                                    const int i = pz - (jlo + qq);                 // >= 1
-                                    if (i <= KL) {
-                                        cplx sq(v[2 * qq], v[2 * qq + 1]);
-                                        addmul(sq, Lc[qq * KL + i - 1], xv);
-                                        v[2 * qq] = sq.x; v[2 * qq + 1] = sq.y;
-                                    }
-                                }
-                            }
-                        }
-                        double w4[4], w2[2], w1;
-                        {
-                            const bool up = lane & 16;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const double send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
-                                w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                            }
-                        }
-                        {
-                            const bool up = lane & 8;
-#pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                const double send = up ? w4[i] : w4[i + 2], keep = up ? w4[i + 2] : w4[i];
-                                w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                            }
-                        }
-                        {
-                            const bool up = lane & 4;
-                            const double send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
-                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
-                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                        // lane 4 i holds component i: (s0.x, s0.y, s1.x, ..., s3.y)
-                        if ((lane & 3) == 0) S.sred[lane >> 2] = w1;
-                        __syncwarp();
-                        if (lane == 0) {
-                            const cplx s0(S.sred[0], S.sred[1]), s1(S.sred[2], S.sred[3]);
-                            const cplx s2(S.sred[4], S.sred[5]), s3(S.sred[6], S.sred[7]);
-                            const cplx *L0 = Lc, *L1 = Lc + KL, *L2 = Lc + 2 * KL;
-                            const cplx x3 = ldv<VG>(x + jlo + 3) - s3;
-                            cplx x2 = ldv<VG>(x + jlo + 2) - s2; submul(x2, L2[0], x3);
-                            cplx x1 = ldv<VG>(x + jlo + 1) - s1; submul(x1, L1[0], x2); submul(x1, L1[1], x3);
-                            cplx x0 = ldv<VG>(x + jlo) - s0; submul(x0, L0[0], x1); submul(x0, L0[1], x2); submul(x0, L0[2], x3);
-                            x[jlo + 3] = x3; x[jlo + 2] = x2; x[jlo + 1] = x1; x[jlo] = x0;
-                        }
-                        __syncwarp();
-                    } else
-                    for (int j = jhi; j >= jlo; --j) {
-                        const int lm = min(KL, N - 1 - j);
-                        const cplx *Lj = Lc + (size_t) (j - jlo) * KL;
-                        cplx s(0.0, 0.0);
-                        for (int i = 1 + lane; i <= lm; i += 32) addmul(s, Lj[i - 1], ldv<VG>(x + j + i));
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
-                            s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
-                        }
-                        if (lane == 0) {
-                            cplx v = ldv<VG>(x + j) - s;
-                            const int l = j + jpv[j];
-                            if (l != j) { const cplx t = ldv<VG>(x + l); x[l] = v; v = t; }
-                            x[j] = v;
-                        }
-                        __syncwarp();
-                    }
-                    // The multipliers of these columns are dead now: drop their (dirty) L2 lines
-                    // instead of letting them be written back to HBM.
-                    if ((CH * KL * sizeof(cplx)) % 128 == 0 && jhi - jlo + 1 == CH) {
-                        const char *g0 = reinterpret_cast<const char *>(Lg + (size_t) jlo * KL);
-                        if ((reinterpret_cast<size_t>(g0) & 127) == 0)
-                        for (int ln = lane; ln < (int) (CH * KL * sizeof(cplx) / 128); ln += 32)
-                            asm volatile("discard.global.L2 [%0], 128;" :: "l"(g0 + (size_t) ln * 128) : "memory");
-                    }
-                    if (lane == 0 && c + NB < nchunk) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        issue(c + NB);
-                    }
-                }
-                chunk_base += nchunk;
-                // state = P^T x (bsmbsm_solver.hpp:274-280)
-                cplx *v = A.state + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
-                for (int e = lane; e < N; e += 32) {
-                    const int f = e / n, y = e - f * n;
-                    v[(size_t) f * A.fs + y] = ldv<VG>(x + 5 * y + f);
-                }
-            }
-            if (lane == 0) {
-                A.info_out[p] = info;
-                if (A.iters_out) A.iters_out[p] = 0;
-            }
-            if (A.ipiv_out)
-                for (int k = lane; k < N; k += 32) A.ipiv_out[(size_t) p * N + k] = k + jpv[k] + 1;
-            __threadfence_block();
-            if (p + 2 * (int) gridDim.x < A.npencil) {
-                if (buf == 0) bar_arrive_n<BAR_EMPTY0>(W::NTH); else bar_arrive_n<BAR_EMPTY1>(W::NTH);
-            }
-        }
+        solver_warp_run<W, VG, false>(A, S, vbase, lwork, lstride, S.ipiv, lane);
         return;
     }
 
@@ -1350,7 +1083,7 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     A.npencil = npencil; A.index = d_index;
     A.state = d_state; A.fs = fs; A.ps = ps;
     A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
-    A.lwork = nullptr; A.vwork = nullptr;
+    A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr;
     A.zero_wall_rhs = zero_wall_rhs;
     if (op->A.KL != op->A.KU) return 1;
     switch (op->A.KL) {
@@ -1403,8 +1136,8 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
                                                       mode ? 3.0 : 0.0);
     count_launch();
     // first pass: x = 0 + (LU)^-T b, in place in the state
-    int rc = invert_pipe_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info,
-                                  nullptr, stream, 1);
+    int rc = invert_fused_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info,
+                                   nullptr, stream, 1);
     if (rc) return rc;
     ResidualArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
@@ -1446,8 +1179,8 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
         SZB_CUDA_OK(cudaStreamSynchronize(stream));
         if (nact == 0) break;
         // d = (LU)^-T r, in place in R (compact layout: field stride n, pencil stride N)
-        rc = invert_pipe_dispatch(op, phi, nact, kma, kna, pos, R, (size_t) n, (size_t) N, nullptr, info2,
-                                  nullptr, stream, 0);
+        rc = invert_fused_dispatch(op, phi, nact, kma, kna, pos, R, (size_t) n, (size_t) N, nullptr, info2,
+                                   nullptr, stream, 0);
         if (rc) return rc;
         if ((rc = residual(nact, pos, kma, kna, slot2, 1, it))) return rc;
     }

@@ -1,0 +1,627 @@
+// invert_sync.cu -- batched invert of (M + phi L), version 5: the fused assemble + zgbtf2 +
+// zgbtrs('T') of invert_pipe.cu (v4) re-scheduled for throughput instead of for one short chain.
+//
+// Replaces the hot loop of invert_mass_plus_scaled_operator
+// (apps/perfect/operator_hybrid_isothermal.cpp:617-686) for the zgbsv solver specification:
+// suzerain_rholut_imexop_packf (rholut_imexop.def:41-597) + IsothermalPATPTEnforcer::op/rhs
+// (:470-525) + bsmbsm_solver::supply_B / zgbtrf + zgbtrs('T') / demand_X
+// (bsmbsm_solver.cpp:155-182).  The matrix never touches HBM.
+//
+// v4 hides the panel factorisation of one pencil behind its own trailing update with twelve
+// warps in fixed roles and 113 KB of shared memory: two pencils per SM, each a chain of named
+// barriers (FP64 pipe 15 % busy).  v5 keeps the arithmetic and gives the latency hiding to the
+// hardware: a CTA is small enough (75 KB at order 8: window with an odd column pitch, ONE set of
+// multipliers, a coefficient ring of exactly 2 kb + 1 points, b / y / x in a global scratch read at
+// L2) that three of them share an SM, and inside a CTA the panel of five columns goes through
+// plain phases separated by three barriers:
+//
+//   F(t)  panel warps: the five columns of collocation point t in registers, one window row per
+//         lane.  The panel is SPECULATED to need no interchange (98 % of the columns of a
+//         turbulent-channel operator): the pivot row of column k is then known in advance to be
+//         the lane holding row j + k, so a column step is a handful of shuffles from that lane
+//         (its row tail, the reciprocal it prepared, its |re| + |im|) -- no pivot search on the
+//         chain, no shared-memory hand-shake between the two panel warps (the second warp keeps
+//         shadow copies of the five pivot rows in spare lanes).  Every lane checks izamax's rule
+//         on the side (no later candidate strictly larger, pivot comfortably scaled); if any
+//         check fails the panel is redone by the exact path: unblocked zgbtf2 on the panel in
+//         shared memory with full 64-bit keys, first maximum, Smith reciprocal, zgbtrf's info.
+//         Meanwhile the other warps fetch the next coefficient point and operator rows.
+//   X/U(t) every warp owns whole trailing columns (cyclically): lanes 0-4 turn the pivot rows
+//         of its columns into rows of U (unit lower 5 x 5 solve), then lane = row applies the
+//         rank-5 update to five columns at once (ten independent FMA chains per lane, the
+//         lane's own multipliers in registers, pivot-row entries by broadcast loads).
+//   A(t)  the five rows entering the window are assembled straight into the slots of the five
+//         retired pivot rows; recycled column slots are zeroed / refilled with b.
+//
+// Rows are kept in logical order (interchanges are physical swaps of window rows, done only by
+// the exact path), so no slot indirection is needed.  The solver warp (L^T sweep of the slot's
+// previous pencil, multipliers streamed back by TMA bulk copies) is v4's.
+//
+// Arithmetic per element is the same sequence of FMAs as the unblocked zgbtf2 sweep; the pivot
+// rule is izamax's (first maximum of |re|+|im|), so ipiv is LAPACK's.
+#include <cstdio>
+#include <cstdlib>
+
+#include "invert_fused.cuh"
+
+// Optional phase timing (make PROF=1): per-phase clock64() deltas of thread 0 (panel warp 0) in
+// slots 0..6 and of the first thread of the first non-panel warp in slots 8..14, summed over all
+// pencils and CTAs; slot 7 counts exact-path panels, slot 15 all panels.  szb_debug_sync_prof().
+#ifdef SZB_PIPE_PROF
+__device__ unsigned long long g_sync_prof[16];
+#define SPROF_DECL long long pt0_ = clock64(); long long pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SPROF_MARK(i) do { const long long t_ = clock64(); pacc_[i] += t_ - pt0_; pt0_ = t_; } while (0)
+#define SPROF_COUNT(i, n) do { pacc_[i] += (n); } while (0)
+#define SPROF_FLUSH(base) do { for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_sync_prof[(base) + i_], (unsigned long long) pacc_[i_]); } while (0)
+#else
+#define SPROF_DECL
+#define SPROF_MARK(i)
+#define SPROF_COUNT(i, n)
+#define SPROF_FLUSH(base)
+#endif
+
+namespace szb {
+
+namespace {
+
+using namespace fused;
+
+template <int KL_, int MINB_>
+struct SyncCfg {
+    static constexpr int MINB = MINB_;              // CTAs per SM the register budget is sized for
+    static constexpr int KL = KL_, KU = KL_, KV = 2 * KL_;
+    static constexpr int KB = (KL_ + 1) / P - 1;    // block half bandwidth of the B-spline operators (k - 2)
+    static constexpr int RW = KL_ + P + 1;          // matrix rows in the window (5 k)
+    static constexpr int NS = RW + 1;               // + the right-hand-side row (position RW)
+    static constexpr int NWP = NS > 32 ? 2 : 1;     // panel warps: one window row per lane
+    static constexpr int SH0 = 27;                  // panel warp 1: lanes SH0.. shadow the five pivot rows
+    static constexpr int CW = (KV + P + 1) | 1;     // column slots: odd pitch (no bank conflicts down a column), multiple of 5
+    static constexpr int CR = 2 * KB + 1;           // coefficient ring: exactly the points one block row needs
+    static constexpr int NCOEF = 75;
+    static constexpr int LDMAX = 20;                // >= ld of the B-spline operators (2k - 3 <= 17)
+    static constexpr int NWC = 7;                   // compute warps; warp NWC is the solver warp
+    static constexpr int NT = 32 * NWC, NTH = NT + 32;
+    static constexpr int NCH = 5;                   // trailing columns a warp updates at once
+    static constexpr int NR = RW - P + 1;           // rows of the trailing update (incl. the right-hand side)
+    static constexpr int NMAIN = NR < 32 ? NR : 32, NTAIL = NR - NMAIN;
+    static constexpr int CH = 4, NB = 2;            // solver: L columns per TMA chunk, ring depth
+    static_assert(KL_ == P * (KB + 1) - 1, "KL = 5 (kb + 1) - 1");
+    static_assert(RW % P == 0 && CW % P == 0, "rows and column slots come in groups of five");
+    static_assert(NS - 32 <= SH0 && SH0 + P <= 32, "room for the shadow lanes");
+};
+
+template <class W>
+struct SSmem {
+    cplx *win;        // [NS][CW]        the window: row r in slot r mod RW, column c in slot c mod CW
+    cplx *lp;         // [NS][P]         multipliers of the current panel by row position
+    cplx *coef;       // [CR][75]        per-point block coefficients
+    cplx *alpha;      // [MAXTERMS]
+    cplx *lring;      // [NB][CH*KL]     multipliers prefetched by TMA for the solver warp
+    double *drow;     // [3][LDMAX]      operator rows of the block row assembled in this iteration
+    double *sred;     // [8]             solver warp
+    unsigned long long *mbar;   // [NB]
+    int *misc;        // [0..1] info per buffer, [4] panel info, [8..9] panel warp w wants the exact path, [10] any interchange,
+                      // [11] ju of the exact path, [12..16] pivot positions of the exact path, [20..27] exact keys {key, pos} per warp
+    unsigned char *tref;   // [MAXTERMS]
+    unsigned char *tblk;   // [76]
+    unsigned char *ipiv;   // [2][N]     (shared-memory variant only)
+};
+
+template <class W>
+struct SyncLayout {
+    static constexpr size_t C = sizeof(cplx);
+    static constexpr size_t win = 0;
+    static constexpr size_t lp = win + C * W::NS * W::CW;
+    static constexpr size_t coef = lp + C * W::NS * P;
+    static constexpr size_t alpha = coef + C * W::CR * W::NCOEF;
+    static constexpr size_t lring = alpha + C * MAXTERMS;
+    static constexpr size_t drow = lring + C * W::NB * W::CH * W::KL;
+    static constexpr size_t sred = drow + 8 * 3 * W::LDMAX;
+    static constexpr size_t mbar = sred + 8 * 8;
+    static constexpr size_t misc = mbar + 8 * W::NB;
+    static constexpr size_t tref = misc + 4 * 32;
+    static constexpr size_t tblk = tref + MAXTERMS;
+    static constexpr size_t ipiv = (tblk + 80 + 15) / 16 * 16;
+    __host__ __device__ static constexpr size_t bytes(int N, bool ig) { return ig ? ipiv : (ipiv + 2 * (size_t) N + 15) / 16 * 16; }
+};
+
+template <class W>
+__device__ __forceinline__ SSmem<W> sync_carve(unsigned char *raw)
+{
+    using Y = SyncLayout<W>;
+    SSmem<W> S;
+    S.win = reinterpret_cast<cplx *>(raw + Y::win);
+    S.lp = reinterpret_cast<cplx *>(raw + Y::lp);
+    S.coef = reinterpret_cast<cplx *>(raw + Y::coef);
+    S.alpha = reinterpret_cast<cplx *>(raw + Y::alpha);
+    S.lring = reinterpret_cast<cplx *>(raw + Y::lring);
+    S.drow = reinterpret_cast<double *>(raw + Y::drow);
+    S.sred = reinterpret_cast<double *>(raw + Y::sred);
+    S.mbar = reinterpret_cast<unsigned long long *>(raw + Y::mbar);
+    S.misc = reinterpret_cast<int *>(raw + Y::misc);
+    S.tref = raw + Y::tref;
+    S.tblk = raw + Y::tblk;
+    S.ipiv = raw + Y::ipiv;
+    return S;
+}
+
+constexpr int BAR_ALL = 1, BAR_PP = 7;
+
+__device__ __forceinline__ cplx ldcg_c(const cplx *p)
+{
+    const double2 t = __ldcg(reinterpret_cast<const double2 *>(p));
+    return cplx(t.x, t.y);
+}
+
+// coefficient points y0 .. y0 + ny - 1, all threads of the caller's group
+template <class W, class SM>
+__device__ __forceinline__ void compute_coef_range(const PackArgs &A, const SM &S, int y0, int ny, int t0, int nt)
+{
+    for (int e = t0; e < ny * W::NCOEF; e += nt) {
+        const int yy = e / W::NCOEF, idx = e - yy * W::NCOEF, y = y0 + yy;
+        if (y >= A.n) continue;
+        const int tb = S.tblk[idx], te = S.tblk[idx + 1];
+        cplx c(0.0, 0.0);
+        for (int t = tb; t < te; ++t) c += S.alpha[t] * __ldg(A.refs + (size_t) S.tref[t] * A.n + y);
+        S.coef[coef_index<W>(y, idx / 15, (idx / 3) % 5, idx % 3)] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F(t), speculative: no interchange in this panel.  Lane -> window row position s (row j + s):
+// panel warp 0 holds positions 0..31, panel warp 1 positions 32..NS-1 and, in lanes SH0..SH0+4,
+// shadow copies of positions 0..4 (the pivot rows), so that neither warp ever waits for the
+// other.  Returns whether this warp saw a reason to redo the panel exactly.
+// ---------------------------------------------------------------------------------------------
+template <class W, class SM>
+__device__ __forceinline__ bool panel_fast(const SM &S, cplx *Lg, cplx *sv, unsigned char *jpv, int j, int jr, int jc,
+                                           int N, int lane, int pw)
+{
+    constexpr int KL = W::KL, RW = W::RW, NS = W::NS, CW = W::CW;
+    int s = lane + 32 * pw;
+    const bool shadow = pw == 1 && lane >= W::SH0;
+    if (shadow) s = lane - W::SH0;
+    const bool has = shadow ? s < P : s < NS;
+    const bool real = has && !shadow;
+    const bool isrhs = real && s == RW, ismat = real && s < RW;
+    int slot = RW;
+    if (s < RW) { slot = jr + s; if (slot >= RW) slot -= RW; }
+    cplx a[P];
+    {
+        const cplx *src = S.win + (size_t) (has ? slot : 0) * CW + jc;
+#pragma unroll
+        for (int m = 0; m < P; ++m) a[m] = has ? src[m] : cplx(0.0, 0.0);
+    }
+    const int src0 = pw == 0 ? 0 : W::SH0;
+    cplx *lps = S.lp + (size_t) (real ? s : 0) * P;
+    bool bad = false;
+#pragma unroll 1
+    for (int k = 0; k < P; ++k) {
+        const int col = j + k;
+        // every lane prepares the reciprocal of its own entry of column k (only the pivot lane's is used)
+        const double mag = cabs1(a[0]);
+        const double r = rcp_nr(fma(a[0].x, a[0].x, a[0].y * a[0].y));
+        const cplx rs(a[0].x * r, -a[0].y * r);
+        const int src = src0 + k;
+        const cplx rinv = shfl_c(rs, src);
+        const double pm = __shfl_sync(0xffffffffu, mag, src);
+        cplx pv[P];
+#pragma unroll
+        for (int m = 1; m < P; ++m) pv[m] = shfl_c(a[m], src);
+        // izamax over rows col..col+KL: the diagonal stays the pivot iff no later candidate is
+        // strictly larger; its magnitude must allow conj(z) / |z|^2 (no over/underflow, not zero, not NaN)
+        const bool cand = ismat && s > k && s <= k + KL && j + s < N;
+        bad |= cand && mag > pm;
+        bad |= !(pm > 1e-140 && pm < 1e140);
+        cplx l = a[0] * rinv;
+        if (!(has && s > k)) l = cplx(0.0, 0.0);
+        if (real) lps[k] = l;
+        if (cand) Lg[(size_t) col * KL + (s - k - 1)] = l;            // zgbtf2 order
+        if (isrhs) sv[col] = l;                                       // y = b^T U^-1
+        if (pw == 0 && lane == 0) jpv[col] = 0;
+#pragma unroll
+        for (int m = 1; m < P; ++m) {
+            cplx t = a[m];
+            submul(t, l, pv[m]);
+            a[m - 1] = t;
+        }
+    }
+    return __any_sync(0xffffffffu, bad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// F(t), exact: unblocked zgbtf2 on the panel in shared memory (S.lp doubles as the working copy,
+// one row position per thread of the panel warps).  izamax's first maximum of the full 64-bit
+// |re|+|im|; interchanges swap whole rows of the working copy (so that its multipliers follow
+// the rows, as the trailing update needs them) while the multipliers go to the scratch in
+// zgbtf2's unswapped order; a zero pivot ends the factorisation with zgbtrf's info.
+// ---------------------------------------------------------------------------------------------
+template <class W, class SM>
+__device__ __noinline__ void panel_slow(const SM &S, cplx *Lg, cplx *sv, unsigned char *jpv, int j, int jr, int jc,
+                                        int N, int t)
+{
+    constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NTP = 32 * W::NWP;
+    const int s = t, lane = t & 31, pw = t >> 5;
+    const bool has = s < NS, ismat = s < RW, isrhs = s == RW;
+    int slot = RW;
+    if (s < RW) { slot = jr + s; if (slot >= RW) slot -= RW; }
+    if (has) {
+#pragma unroll
+        for (int m = 0; m < P; ++m) S.lp[s * P + m] = S.win[(size_t) slot * CW + jc + m];
+    }
+    if (t == 0) { S.misc[10] = 0; S.misc[11] = 0; }
+    bar_sync_n<BAR_PP>(NTP);
+    int jumax = 0, anyswap = 0;
+    for (int k = 0; k < P; ++k) {
+        const int col = j + k;
+        const bool cand = ismat && s >= k && s <= k + KL && j + s < N;
+        const long long key = cand ? __double_as_longlong(cabs1(S.lp[s * P + k])) : -1ll;
+        const int e = exact_pivot(key, -1ll, cand ? s : INT_MAX, INT_MAX);
+        const int srcl = e & 0xff;
+        long long kw = __shfl_sync(0xffffffffu, key, srcl);
+        int sw = __shfl_sync(0xffffffffu, cand ? s : INT_MAX, srcl);
+        if (kw < 0) sw = INT_MAX;
+        if (lane == 0) {
+            S.misc[20 + 4 * pw] = (int) (kw & 0xffffffffll);
+            S.misc[21 + 4 * pw] = (int) (kw >> 32);
+            S.misc[22 + 4 * pw] = sw;
+        }
+        bar_sync_n<BAR_PP>(NTP);
+        long long kwin = (long long) (unsigned) S.misc[20] | (long long) S.misc[21] << 32;
+        int w = S.misc[22];
+        if (W::NWP == 2) {
+            const long long k1 = (long long) (unsigned) S.misc[24] | (long long) S.misc[25] << 32;
+            const int s1 = S.misc[26];
+            if (k1 > kwin || (k1 == kwin && s1 < w)) { kwin = k1; w = s1; }
+        }
+        if (kwin <= 0) {                                   // |re|+|im| == 0 (or no candidate): zero pivot
+            if (t == 0) { S.misc[4] = col + 1; jpv[col] = 0; }
+            break;
+        }
+        if (t == 0) { jpv[col] = (unsigned char) (w - k); S.misc[12 + k] = w; }
+        jumax = max(jumax, j + w + KU);
+        anyswap |= w != k;
+        if (w != k && t < P) {
+            const cplx x0 = S.lp[k * P + t], x1 = S.lp[w * P + t];
+            S.lp[k * P + t] = x1; S.lp[w * P + t] = x0;
+        }
+        bar_sync_n<BAR_PP>(NTP);
+        if (has && s > k) {
+            const cplx rinv = recip_fast(S.lp[k * P + k]);
+            const cplx l = S.lp[s * P + k] * rinv;
+            S.lp[s * P + k] = l;
+#pragma unroll
+            for (int m = 1; m < P; ++m)
+                if (m > k) { cplx x = S.lp[s * P + m]; submul(x, l, S.lp[k * P + m]); S.lp[s * P + m] = x; }
+            if (ismat && s <= k + KL && j + s < N) Lg[(size_t) col * KL + (s - k - 1)] = l;
+            if (isrhs) sv[col] = l;
+        }
+        bar_sync_n<BAR_PP>(NTP);
+    }
+    if (t == 0) { S.misc[10] = anyswap; S.misc[11] = jumax; }
+}
+
+template <class W, bool IG>
+__global__ void __launch_bounds__(W::NTH, W::MINB)
+invert_sync_kernel(const PipeArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const PackArgs &K = A.pk;
+    const int N = K.N, n = K.n;
+    const SSmem<W> S = sync_carve<W>(smem_raw);
+    const int tid = threadIdx.x;
+    constexpr int KL = W::KL, KU = W::KU, KB = W::KB, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NWC = W::NWC, NCH = W::NCH;
+    cplx *const vbase = A.vwork + (size_t) blockIdx.x * 2 * N;
+    unsigned char *const ipbase = IG ? A.ipwork + (size_t) blockIdx.x * 2 * N : S.ipiv;
+    const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
+    cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
+
+    for (int t = tid; t < MAXTERMS; t += W::NTH) S.tref[t] = K.terms->ref[t];
+    for (int t = tid; t <= NBLOCK; t += W::NTH) S.tblk[t] = K.terms->blk_begin[t];
+    if (tid == NT) {
+        for (int b = 0; b < W::NB; ++b) mbar_init(S.mbar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= NT) {
+        // =================== solver warp: L^T back substitution ===================
+        solver_warp_run<W, true, IG>(A, S, vbase, lwork, lstride, ipbase, tid - NT);
+        return;
+    }
+
+    // ============================ compute warps ============================
+    const int lane = tid & 31, warp = tid >> 5;
+    int q = 0;
+    for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
+        const int buf = q & 1;
+        if (q >= 2) { if (buf == 0) bar_sync_n<BAR_EMPTY0>(W::NTH); else bar_sync_n<BAR_EMPTY1>(W::NTH); }
+        cplx *sv = vbase + (size_t) buf * N;
+        unsigned char *jpv = ipbase + (size_t) buf * N;
+        cplx *Lg = lwork + (size_t) buf * lstride;
+        const double km = K.km[p], kn = K.kn[p];
+
+        // b = P state with the wall rows zeroed (bsmbsm_solver.hpp:150-156,
+        // operator_hybrid_isothermal.cpp:516-525)
+        {
+            const cplx *v = A.state + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
+            for (int e = tid; e < N; e += NT) {
+                const int f = e / n, y = e - f * n;
+                cplx val = v[(size_t) f * A.fs + y];
+                if (K.with_bc && A.zero_wall_rhs && f < 4
+                    && ((y == 0 && K.wall_begin == 0) || (y == n - 1 && K.wall_end == 2)))
+                    val = cplx(0.0, 0.0);
+                sv[5 * y + f] = val;
+            }
+        }
+        for (int t = tid; t < K.terms->nterms; t += NT)
+            S.alpha[t] = wave_factor(K.terms->wave[t], km, kn) * K.terms->sc[t];
+        if (tid == 0) { S.misc[buf] = 0; S.misc[4] = 0; }
+        bar_sync_n<BAR_ALL>(NT);
+        // initial window: rows 0..RW-1 in slots 0..RW-1.  The ring holds points 0..2kb first (block rows
+        // 0..kb), then point 2kb+1 replaces point 0 for block row kb+1 (= RW/5 - 1).
+        compute_coef_range<W>(K, S, 0, W::CR, tid, NT);
+        bar_sync_n<BAR_ALL>(NT);
+        for (int blk = 0; blk <= KB; ++blk)
+            assemble_block<W>(K, S, km, kn, blk, S.win + (size_t) blk * P * CW, tid, NT);
+        // right-hand-side row: t_c = b_c
+        for (int c = tid; c < CW; c += NT) S.win[(size_t) RW * CW + c] = c < N ? ldcg_c(sv + c) : cplx(0.0, 0.0);
+        bar_sync_n<BAR_ALL>(NT);
+        compute_coef_range<W>(K, S, W::CR, 1, tid, NT);
+        bar_sync_n<BAR_ALL>(NT);
+        assemble_block<W>(K, S, km, kn, KB + 1, S.win + (size_t) (KB + 1) * P * CW, tid, NT);
+        bar_sync_n<BAR_ALL>(NT);
+
+        int info = 0, ju = 0, jr = 0, jc = 0;
+        SPROF_DECL
+        for (int j = 0; j < N; j += P) {
+            const int yI = (j + RW) / P;                    // block row entering after this panel
+            // ---------------- F(t) | next coefficient point, operator rows ----------------
+            if (warp < W::NWP) {
+                const bool bad = panel_fast<W>(S, Lg, sv, jpv, j, jr, jc, N, lane, warp);
+                if (lane == 0) S.misc[8 + warp] = bad;
+                if (W::NWP == 1 && tid == 0) S.misc[9] = 0;
+            } else {
+                constexpr int NTO = NT - 32 * W::NWP;
+                const int to = tid - 32 * W::NWP;
+                compute_coef_range<W>(K, S, yI + KB, 1, to, NTO);
+                for (int i = to; i < 3 * K.ld; i += NTO) {
+                    const int d = i / K.ld, r = i - d * K.ld, yJ = yI - r + K.ku;
+                    S.drow[i] = (yJ >= 0 && yJ < n) ? __ldg(K.D + (size_t) (d * K.ld + r) * n + yJ) : 0.0;
+                }
+            }
+            SPROF_MARK(0);
+            bar_sync_n<BAR_ALL>(NT);
+            SPROF_MARK(1);
+            SPROF_COUNT(7, 1);
+            int juc = j + P - 1 + KU;
+            if (S.misc[8] | S.misc[9]) {
+                SPROF_COUNT(6, 1);
+                if (warp < W::NWP) panel_slow<W>(S, Lg, sv, jpv, j, jr, jc, N, tid);
+                bar_sync_n<BAR_ALL>(NT);
+                info = S.misc[4];
+                if (info) break;
+                juc = S.misc[11];
+                if (S.misc[10]) {
+                    // the panel's interchanges on the trailing columns, in order (zgbtf2's zswap to the right)
+                    const int ncs = min(max(ju, juc), N - 1) - (j + P) + 1;
+                    for (int c = tid; c < ncs; c += NT) {
+                        int cs = jc + P + c; if (cs >= CW) cs -= CW;
+#pragma unroll
+                        for (int k = 0; k < P; ++k) {
+                            const int w = S.misc[12 + k];
+                            if (w != k) {
+                                int sw = jr + w; if (sw >= RW) sw -= RW;
+                                const cplx x0 = S.win[(size_t) (jr + k) * CW + cs], x1 = S.win[(size_t) sw * CW + cs];
+                                S.win[(size_t) (jr + k) * CW + cs] = x1; S.win[(size_t) sw * CW + cs] = x0;
+                            }
+                        }
+                    }
+                    bar_sync_n<BAR_ALL>(NT);
+                }
+            }
+            ju = max(ju, juc);
+            SPROF_MARK(2);
+            // ---------------- X(t) + U(t): trailing columns j+5 .. ju, warp = columns, lane = row ----------------
+            {
+                const int ncols = min(ju, N - 1) - (j + P) + 1;
+                const int pos = P + lane;                                   // main rows: positions 5 .. 5 + NMAIN - 1
+                int rslot = RW;
+                if (pos < RW) { rslot = jr + pos; if (rslot >= RW) rslot -= RW; }
+                cplx l[P];
+                if (lane < W::NMAIN) {
+#pragma unroll
+                    for (int k = 0; k < P; ++k) l[k] = S.lp[pos * P + k];
+                }
+                const cplx *prow = S.win + (size_t) jr * CW;                // the five pivot rows
+                for (int m0 = 0; warp + NWC * m0 < ncols; m0 += NCH) {
+                    // X: lanes 0..NCH-1, one column each
+                    if (lane < NCH) {
+                        const int i = warp + NWC * (m0 + lane);
+                        if (i < ncols) {
+                            int cs = jc + P + i; if (cs >= CW) cs -= CW;
+                            cplx u[P];
+#pragma unroll
+                            for (int k = 0; k < P; ++k) u[k] = prow[k * CW + cs];
+#pragma unroll
+                            for (int k = 1; k < P; ++k) {
+#pragma unroll
+                                for (int i2 = 0; i2 < k; ++i2) submul(u[k], S.lp[k * P + i2], u[i2]);
+                                S.win[(size_t) (jr + k) * CW + cs] = u[k];
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    int cs[NCH];
+#pragma unroll
+                    for (int x = 0; x < NCH; ++x) {
+                        const int i = warp + NWC * (m0 + x);
+                        int c = jc + P + i; if (c >= CW) c -= CW;
+                        cs[x] = i < ncols ? c : -1;
+                    }
+                    if (lane < W::NMAIN) {
+                        cplx w[NCH];
+                        cplx *wrow = S.win + (size_t) rslot * CW;
+#pragma unroll
+                        for (int x = 0; x < NCH; ++x) w[x] = cs[x] >= 0 ? wrow[cs[x]] : cplx(0.0, 0.0);
+#pragma unroll
+                        for (int k = 0; k < P; ++k) {
+#pragma unroll
+                            for (int x = 0; x < NCH; ++x) {
+                                const cplx uk = prow[k * CW + max(cs[x], 0)];
+                                submul(w[x], l[k], uk);
+                            }
+                        }
+#pragma unroll
+                        for (int x = 0; x < NCH; ++x) if (cs[x] >= 0) wrow[cs[x]] = w[x];
+                    }
+                    // tail rows (positions 5 + NMAIN .. RW): one element per lane
+                    if (W::NTAIL > 0) {
+                        for (int e = lane; e < W::NTAIL * NCH; e += 32) {
+                            const int x = e / W::NTAIL, r = e - x * W::NTAIL;
+                            const int i = warp + NWC * (m0 + x);
+                            if (i < ncols) {
+                                int c = jc + P + i; if (c >= CW) c -= CW;
+                                const int tp = P + W::NMAIN + r;
+                                int ts = RW;
+                                if (tp < RW) { ts = jr + tp; if (ts >= RW) ts -= RW; }
+                                cplx w = S.win[(size_t) ts * CW + c];
+#pragma unroll
+                                for (int k = 0; k < P; ++k) submul(w, S.lp[tp * P + k], prow[k * CW + c]);
+                                S.win[(size_t) ts * CW + c] = w;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            SPROF_MARK(3);
+            bar_sync_n<BAR_ALL>(NT);
+            SPROF_MARK(4);
+            // ---------------- A(t): rows j+RW .. j+RW+4 replace the retired pivot rows; column slots
+            // jc .. jc+4 now stand for columns j+CW .. j+CW+4 ----------------
+            {
+                cplx *dst = S.win + (size_t) jr * CW;
+                if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
+                    assemble_block_interior<W>(K, S, S.drow, yI, dst, tid, NT);
+                else
+                    assemble_block<W>(K, S, km, kn, yI, dst, tid, NT);
+                for (int e = tid; e < (NS - P) * P; e += NT) {
+                    const int sp = e / P, m = e - sp * P, pos = P + sp;
+                    int slot = RW;
+                    if (pos < RW) { slot = jr + pos; if (slot >= RW) slot -= RW; }
+                    cplx val(0.0, 0.0);
+                    if (pos == RW) { const int cn = j + CW + m; if (cn < N) val = ldcg_c(sv + cn); }
+                    S.win[(size_t) slot * CW + jc + m] = val;
+                }
+            }
+            SPROF_MARK(5);
+            bar_sync_n<BAR_ALL>(NT);
+            SPROF_MARK(1);
+            jr += P; if (jr >= RW) jr -= RW;
+            jc += P; if (jc >= CW) jc -= CW;
+        }
+#ifdef SZB_PIPE_PROF
+        if (tid == 0) SPROF_FLUSH(0);
+        if (tid == 32 * W::NWP) SPROF_FLUSH(8);
+#endif
+        if (tid == 0) { S.misc[buf] = info; if (info) for (int k = 0; k < N; ++k) jpv[k] = 0; }
+        __threadfence();
+        if (buf == 0) bar_arrive_n<BAR_FULL0>(W::NTH); else bar_arrive_n<BAR_FULL1>(W::NTH);
+    }
+}
+
+template <class W, bool IG>
+int launch_sync_ig(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
+{
+    const int N = op->A.N;
+    const size_t smem = SyncLayout<W>::bytes(N, IG);
+    if (smem > 227 * 1024) return 1;                 // caller falls back to another kernel
+    static bool configured = false;
+    if (!configured) {
+        SZB_CUDA_OK(cudaFuncSetAttribute(invert_sync_kernel<W, IG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    int per_sm = 0;
+    SZB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, invert_sync_kernel<W, IG>, W::NTH, smem));
+    if (per_sm < 1) return 1;
+    static const bool debug = std::getenv("SZB_PIPE_DEBUG") != nullptr;
+    if (debug)
+        std::fprintf(stderr, "invert_sync: KL=%d N=%d ig=%d threads=%d smem=%zu CTAs/SM=%d\n", W::KL, N, (int) IG, W::NTH, smem, per_sm);
+    int slots = op->sm_count * per_sm;
+    if (slots > npencil) slots = npencil;
+    const size_t lbytes = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
+    const size_t vbytes = (size_t) slots * 2 * N * sizeof(cplx);
+    const size_t ibytes = IG ? (((size_t) slots * 2 * N + 255) & ~(size_t) 255) : 0;
+    const size_t need = lbytes + vbytes + ibytes;
+    if (need > op->work_bytes) {
+        if (op->d_work) SZB_CUDA_OK(cudaFree(op->d_work));
+        op->d_work = nullptr; op->work_bytes = 0;
+        SZB_CUDA_OK(cudaMalloc(&op->d_work, need));
+        op->work_bytes = need;
+    }
+    op->work_slots = slots;
+    unsigned char *w = static_cast<unsigned char *>(op->d_work);
+    A.lwork = reinterpret_cast<cplx *>(w);
+    A.vwork = reinterpret_cast<cplx *>(w + lbytes);
+    A.ipwork = IG ? w + lbytes + vbytes : nullptr;
+    invert_sync_kernel<W, IG><<<slots, W::NTH, smem, stream>>>(A);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// The pivot offsets (2 N bytes per CTA) stay in shared memory while MINB CTAs still fit an SM with
+// them; for long pencils they move to the global scratch.
+template <class W>
+int launch_sync(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
+{
+    if (op->kl != W::KB || op->ku != W::KB) return 1;
+    const size_t per_cta = (233472 - (size_t) W::MINB * 1024) / W::MINB;
+    if (SyncLayout<W>::bytes(op->A.N, false) > per_cta)
+        return launch_sync_ig<W, true>(op, A, npencil, stream);
+    return launch_sync_ig<W, false>(op, A, npencil, stream);
+}
+
+}  // namespace
+
+// Returns 0 when launched, 1 when this (kl, ku) / size has no instantiation (the caller then
+// uses another kernel), <0 on error.
+int invert_sync_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                         const double *d_km, const double *d_kn, const int *d_index,
+                         cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs)
+{
+    PipeArgs A;
+    fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
+    A.npencil = npencil; A.index = d_index;
+    A.state = d_state; A.fs = fs; A.ps = ps;
+    A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
+    A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr;
+    A.zero_wall_rhs = zero_wall_rhs;
+    if (op->A.KL != op->A.KU) return 1;
+    switch (op->A.KL) {
+    case 14: return launch_sync<SyncCfg<14, 3>>(op, A, npencil, stream);     // k = 4
+    case 24: return launch_sync<SyncCfg<24, 3>>(op, A, npencil, stream);     // k = 6
+    case 34: return launch_sync<SyncCfg<34, 3>>(op, A, npencil, stream);     // k = 8
+    case 44: return launch_sync<SyncCfg<44, 2>>(op, A, npencil, stream);     // k = 10
+    default: return 1;
+    }
+}
+
+}  // namespace szb
+
+// debug hook (not part of the C ABI): phase clocks accumulated by a PROF=1 build
+extern "C" int szb_debug_sync_prof(unsigned long long out[16], int reset)
+{
+#ifdef SZB_PIPE_PROF
+    if (cudaMemcpyFromSymbol(out, g_sync_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_sync_prof, z, sizeof z); }
+    return 1;
+#else
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    (void) reset;
+    return 0;
+#endif
+}

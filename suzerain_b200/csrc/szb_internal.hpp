@@ -25,10 +25,6 @@ void report_cuda(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(unsigned n = 1);
 void field_ctx_free(void *p);      // capi.cu: cached whole-field plan of an operator context
 struct cplx;
-int invert_window_dispatch(const szb_imexop *op, const double phi[2], int npencil,
-                           const double *d_km, const double *d_kn, const int *d_index,
-                           cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                           int *d_iters, cudaStream_t stream);
 int accumulate_launch(const szb_imexop *op, const double phi[2], int npencil, const double *d_km, const double *d_kn,
                       const int *d_index, const int *d_index_out, int out_plain, const szb_complex *d_in, size_t in_fs, size_t in_ps,
                       const double beta[2], szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream);
@@ -36,6 +32,15 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                          int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
+int invert_sync_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                         const double *d_km, const double *d_kn, const int *d_index,
+                         cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
+// the fused zgbsv kernel in use: v5 (invert_sync.cu) unless SZB_INVERT=v4 or v5 has no instantiation
+int invert_fused_dispatch(const szb_imexop *op, const double phi[2], int npencil,
+                          const double *d_km, const double *d_kn, const int *d_index,
+                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                          int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
 int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
@@ -43,11 +48,6 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
 int invert00_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
                       const int *d_index, cplx *d_state, size_t fs, size_t ps, int nextra, cplx *d_extra,
                       int *d_ipiv, int *d_info, int *d_iters, cudaStream_t stream);
-int invert_blocked_dispatch(const szb_imexop *op, const double phi[2], int npencil,
-                            const double *d_km, const double *d_kn, const int *d_index,
-                            cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                            int *d_iters, cudaStream_t stream);
-
 // Term table dimensions (rholut_terms.def)
 enum Field { E = 0, U = 1, V = 2, W = 3, R = 4, NFIELD = 5 };
 enum Oper  { M = 0, D1 = 1, D2 = 2, NOPER = 3 };

@@ -11,6 +11,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsuzerain_b200.so")
+# development only: an instrumented / experimental build of the same library (tools/build_variant.sh)
+if os.environ.get("SZB_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["SZB_LIB"])
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
