@@ -170,6 +170,14 @@ int  szb_imexop_set_scenario(szb_imexop *op, const szb_rholut_imexop_scenario *s
  * 42) into a dense device table. */
 int  szb_imexop_set_refs(szb_imexop *op, const szb_rholut_imexop_ref *r,
                          const szb_rholut_imexop_refld *ld);
+/* The same from a DEVICE copy of the reference's `references` block (42 rows x Ny, column-major,
+ * leading dimension ld >= 31: apps/perfect/references.hpp:82-125), e.g. the buffer a sharded stepper
+ * has just summed over ranks (MPI_Allreduce of apps/perfect/perfect.cpp:1397 -> ncclAllReduce): rows
+ * q::u .. q::e_deltarho are the 26 profiles, in the order of references::rholut_imexop.  Asynchronous
+ * on `stream`; no host copy. */
+#define SZB_REFERENCES_ROWS  42
+#define SZB_REFERENCES_FIRST 5
+int  szb_imexop_set_refs_device(szb_imexop *op, const double *d_references, int ld, void *stream);
 int  szb_imexop_set_isothermal(szb_imexop *op, const szb_isothermal *iso);
 /* 5x5 column-major Giles matrices (upper_nrbc_{a,b,c},
  * operator_hybrid_isothermal.cpp:771-777); any may be NULL. */

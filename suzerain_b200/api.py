@@ -255,6 +255,15 @@ class ImexOp:
         _L.check("szb_imexop_set_refs", _L.load().szb_imexop_set_refs(self.handle, C.byref(r), C.byref(ld)))
         return self
 
+    def set_refs_device(self, references, stream=None):
+        """references: CUDA float64 tensor holding the reference's 42 x Ny column-major `references` block,
+        i.e. shape (Ny, 42) C-contiguous (apps/perfect/references.hpp:82-125) -- what a sharded stepper has
+        just all-reduced (apps/perfect/perfect.cpp:1397).  No host round trip."""
+        assert references.is_cuda and references.shape == (self.n, 42) and references.is_contiguous()
+        _L.check("szb_imexop_set_refs_device",
+                 _L.load().szb_imexop_set_refs_device(self.handle, _ptr(references), 42, _stream_handle(stream)))
+        return self
+
     def set_isothermal(self, enforce_lower=True, enforce_upper=True, lower=(1.0, 0.0, 0.0, 0.0),
                        upper=(1.0, 0.0, 0.0, 0.0)):
         iso = _L.Isothermal(int(enforce_lower), int(enforce_upper), *map(float, lower), *map(float, upper))

@@ -313,6 +313,19 @@ using namespace szb;
 // ---------------------------------------------------------------------------
 // C ABI: context management
 // ---------------------------------------------------------------------------
+namespace szb {
+// references -> dense profile table: rows q::u .. q::e_deltarho of the reference's 42 x Ny column-major
+// `references` block (apps/perfect/references.hpp:82-125) are exactly the 26 profiles of
+// references::rholut_imexop (references.cpp:50-108), in that order.
+__global__ void gather_references_kernel(int n, const double *src, int ld, double *dst)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= SZB_NREF * n) return;
+    const int q = e / n, y = e - q * n;
+    dst[e] = src[(size_t) y * ld + SZB_REFERENCES_FIRST + q];
+}
+}  // namespace szb
+
 extern "C" {
 
 const char *szb_version(void) { return "suzerain_b200 0.1 (sm_100a, FP64)"; }
@@ -427,6 +440,18 @@ int szb_imexop_set_refs(szb_imexop *op, const szb_rholut_imexop_ref *r,
         for (int i = 0; i < n; ++i) h[(size_t) q * n + i] = ptrs[q][(size_t) i * lds[q]];
     }
     SZB_CUDA_OK(cudaMemcpy(op->d_refs, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int szb_imexop_set_refs_device(szb_imexop *op, const double *d_references, int ld, void *stream)
+{
+    if (!op) return -1;
+    if (!d_references) return -2;
+    if (ld < SZB_REFERENCES_FIRST + SZB_NREF) return -3;
+    const int total = SZB_NREF * op->n;
+    szb::gather_references_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t) stream>>>(op->n, d_references, ld, op->d_refs);
+    szb::count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

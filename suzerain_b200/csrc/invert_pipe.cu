@@ -1083,7 +1083,7 @@ int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     A.npencil = npencil; A.index = d_index;
     A.state = d_state; A.fs = fs; A.ps = ps;
     A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
-    A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr;
+    A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr; A.xwork = nullptr;
     A.zero_wall_rhs = zero_wall_rhs;
     if (op->A.KL != op->A.KU) return 1;
     switch (op->A.KL) {

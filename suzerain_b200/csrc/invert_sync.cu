@@ -48,9 +48,20 @@
 // slots 0..6 and of the first thread of the first non-panel warp in slots 8..14, summed over all
 // pencils and CTAs; slot 7 counts exact-path panels, slot 15 all panels.  szb_debug_sync_prof().
 #ifdef SZB_PIPE_PROF
-__device__ unsigned long long g_sync_prof[16];
-#define SPROF_DECL long long pt0_ = clock64(); long long pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define SPROF_MARK(i) do { const long long t_ = clock64(); pacc_[i] += t_ - pt0_; pt0_ = t_; } while (0)
+// work / wait clocks of three threads (first lanes of warps 0, 2, 5), 8 slots each:
+// [P1 work, B1 wait, P2 work, B2 wait, P3 work, B3 wait, exact-path panels, panels]
+__device__ unsigned long long g_sync_prof[24];
+// the clock is read only once a shared-memory load issued after the barrier has returned:
+// bar.sync is DEFER_BLOCKING, a bare clock read would give the arrival time
+__device__ __forceinline__ long long sprof_clock(const int *smem_word)
+{
+    const int d = *reinterpret_cast<const volatile int *>(smem_word);
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(d) : "memory");
+    return t;
+}
+#define SPROF_DECL long long pt0_ = sprof_clock(S.misc); long long pacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SPROF_MARK(i) do { const long long t_ = sprof_clock(S.misc); pacc_[i] += t_ - pt0_; pt0_ = t_; } while (0)
 #define SPROF_COUNT(i, n) do { pacc_[i] += (n); } while (0)
 #define SPROF_FLUSH(base) do { for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_sync_prof[(base) + i_], (unsigned long long) pacc_[i_]); } while (0)
 #else
@@ -78,7 +89,7 @@ struct SyncCfg {
     static constexpr int CW = (KV + P + 1) | 1;     // column slots: odd pitch (no bank conflicts down a column), multiple of 5
     static constexpr int CR = 2 * KB + 1;           // coefficient ring: exactly the points one block row needs
     static constexpr int NCOEF = 75;
-    static constexpr int LDMAX = 20;                // >= ld of the B-spline operators (2k - 3 <= 17)
+    static constexpr int LDMAX = 17;                // >= ld of the B-spline operators (2k - 3 <= 17)
     static constexpr int NWC = 7;                   // compute warps; warp NWC is the solver warp
     static constexpr int NT = 32 * NWC, NTH = NT + 32;
     static constexpr int NCH = 5;                   // trailing columns a warp updates at once
@@ -97,7 +108,11 @@ struct SSmem {
     cplx *coef;       // [CR][75]        per-point block coefficients
     cplx *alpha;      // [MAXTERMS]
     cplx *lring;      // [NB][CH*KL]     multipliers prefetched by TMA for the solver warp
-    double *drow;     // [3][LDMAX]      operator rows of the block row assembled in this iteration
+    cplx *tbu;        // [10]            F1 -> F2: strict upper part of U11, row k at k (9 - k) / 2
+    cplx *tbr;        // [P]             F1 -> F2: reciprocal pivots
+    double *tbm;      // [P]             F1 -> F2: |pivot|_1
+    double *drow;     // [3][LDMAX]      operator rows of the block row assembled in the next P1
+    double *refcol;   // [27]            reference profiles at the coefficient point computed in this P2
     double *sred;     // [8]             solver warp
     unsigned long long *mbar;   // [NB]
     int *misc;        // [0..1] info per buffer, [4] panel info, [8..9] panel warp w wants the exact path, [10] any interchange,
@@ -115,8 +130,12 @@ struct SyncLayout {
     static constexpr size_t coef = lp + C * W::NS * P;
     static constexpr size_t alpha = coef + C * W::CR * W::NCOEF;
     static constexpr size_t lring = alpha + C * MAXTERMS;
-    static constexpr size_t drow = lring + C * W::NB * W::CH * W::KL;
-    static constexpr size_t sred = drow + 8 * 3 * W::LDMAX;
+    static constexpr size_t tbu = lring + C * W::NB * W::CH * W::KL;
+    static constexpr size_t tbr = tbu + C * 10;
+    static constexpr size_t tbm = tbr + C * P;
+    static constexpr size_t drow = tbm + 8 * P + 8;
+    static constexpr size_t refcol = drow + 8 * 3 * W::LDMAX;
+    static constexpr size_t sred = refcol + 8 * (SZB_NREF + 1);
     static constexpr size_t mbar = sred + 8 * 8;
     static constexpr size_t misc = mbar + 8 * W::NB;
     static constexpr size_t tref = misc + 4 * 32;
@@ -135,7 +154,11 @@ __device__ __forceinline__ SSmem<W> sync_carve(unsigned char *raw)
     S.coef = reinterpret_cast<cplx *>(raw + Y::coef);
     S.alpha = reinterpret_cast<cplx *>(raw + Y::alpha);
     S.lring = reinterpret_cast<cplx *>(raw + Y::lring);
+    S.tbu = reinterpret_cast<cplx *>(raw + Y::tbu);
+    S.tbr = reinterpret_cast<cplx *>(raw + Y::tbr);
+    S.tbm = reinterpret_cast<double *>(raw + Y::tbm);
     S.drow = reinterpret_cast<double *>(raw + Y::drow);
+    S.refcol = reinterpret_cast<double *>(raw + Y::refcol);
     S.sred = reinterpret_cast<double *>(raw + Y::sred);
     S.mbar = reinterpret_cast<unsigned long long *>(raw + Y::mbar);
     S.misc = reinterpret_cast<int *>(raw + Y::misc);
@@ -146,6 +169,24 @@ __device__ __forceinline__ SSmem<W> sync_carve(unsigned char *raw)
 }
 
 constexpr int BAR_ALL = 1, BAR_PP = 7;
+
+// barrier BAR_ALL of `count` threads that also ORs a predicate over them
+__device__ __forceinline__ int bar_red_or(int pred, int count)
+{
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %1, 0;\n\tbar.red.or.pred p, 1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(pred), "r"(count) : "memory");
+    return r;
+}
+
+// a shared-memory load ptxas keeps in program order relative to the other volatile accesses
+// (it otherwise re-serialises a software-pipelined loop to save registers)
+__device__ __forceinline__ cplx lds_cv(unsigned sa)
+{
+    cplx v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sa) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ cplx ldcg_c(const cplx *p)
 {
@@ -168,65 +209,121 @@ __device__ __forceinline__ void compute_coef_range(const PackArgs &A, const SM &
 }
 
 // ---------------------------------------------------------------------------------------------
-// F(t), speculative: no interchange in this panel.  Lane -> window row position s (row j + s):
-// panel warp 0 holds positions 0..31, panel warp 1 positions 32..NS-1 and, in lanes SH0..SH0+4,
-// shadow copies of positions 0..4 (the pivot rows), so that neither warp ever waits for the
-// other.  Returns whether this warp saw a reason to redo the panel exactly.
+// F1(t), speculative: the 5 x 5 diagonal block of the panel, rows j..j+4 in lanes 0..4 of the
+// panel warp, assuming no interchange: the pivot row of column k is lane k, so a column step is a
+// handful of shuffles from that lane (its row tail, the reciprocal it prepared, its |re|+|im|).
+// Publishes the rows of U11 (strict upper part), the reciprocal pivots and the pivot magnitudes
+// for F2, the multipliers L11 to S.lp and the scratch.  Returns whether the block needs the exact path.
 // ---------------------------------------------------------------------------------------------
 template <class W, class SM>
-__device__ __forceinline__ bool panel_fast(const SM &S, cplx *Lg, cplx *sv, unsigned char *jpv, int j, int jr, int jc,
-                                           int N, int lane, int pw)
+__device__ __forceinline__ bool panel_top(const SM &S, cplx *Lcol, unsigned char *jpv, int j, int jr, int jc, int lane)
 {
-    constexpr int KL = W::KL, RW = W::RW, NS = W::NS, CW = W::CW;
-    int s = lane + 32 * pw;
-    const bool shadow = pw == 1 && lane >= W::SH0;
-    if (shadow) s = lane - W::SH0;
-    const bool has = shadow ? s < P : s < NS;
-    const bool real = has && !shadow;
-    const bool isrhs = real && s == RW, ismat = real && s < RW;
-    int slot = RW;
-    if (s < RW) { slot = jr + s; if (slot >= RW) slot -= RW; }
+    constexpr int KL = W::KL, CW = W::CW;
+    const int s = lane;
+    const bool has = s < P;
     cplx a[P];
     {
-        const cplx *src = S.win + (size_t) (has ? slot : 0) * CW + jc;
+        const cplx *src = S.win + (size_t) (jr + (has ? s : 0)) * CW + jc;
 #pragma unroll
         for (int m = 0; m < P; ++m) a[m] = has ? src[m] : cplx(0.0, 0.0);
     }
-    const int src0 = pw == 0 ? 0 : W::SH0;
-    cplx *lps = S.lp + (size_t) (real ? s : 0) * P;
+    const unsigned lp_sa = smem_u32(S.lp + s * P), tb_sa = smem_u32(S.tbu), tr_sa = smem_u32(S.tbr), tm_sa = smem_u32(S.tbm);
+    cplx *Lrow = Lcol + s;
     bool bad = false;
-#pragma unroll 1
+    // fully unrolled: every index below is a compile-time constant (the chain of one column step is
+    // |a_kk|^2 -> reciprocal -> shuffle -> multiplier -> update of the next pivot candidate)
+#pragma unroll
     for (int k = 0; k < P; ++k) {
-        const int col = j + k;
-        // every lane prepares the reciprocal of its own entry of column k (only the pivot lane's is used)
-        const double mag = cabs1(a[0]);
-        const double r = rcp_nr(fma(a[0].x, a[0].x, a[0].y * a[0].y));
-        const cplx rs(a[0].x * r, -a[0].y * r);
-        const int src = src0 + k;
-        const cplx rinv = shfl_c(rs, src);
-        const double pm = __shfl_sync(0xffffffffu, mag, src);
+        const double mag = cabs1(a[k]);
+        const double r = rcp_nr(fma(a[k].x, a[k].x, a[k].y * a[k].y));
+        const cplx rs(a[k].x * r, -a[k].y * r);
+        const cplx rinv = shfl_c(rs, k);
         cplx pv[P];
 #pragma unroll
-        for (int m = 1; m < P; ++m) pv[m] = shfl_c(a[m], src);
-        // izamax over rows col..col+KL: the diagonal stays the pivot iff no later candidate is
-        // strictly larger; its magnitude must allow conj(z) / |z|^2 (no over/underflow, not zero, not NaN)
-        const bool cand = ismat && s > k && s <= k + KL && j + s < N;
-        bad |= cand && mag > pm;
-        bad |= !(pm > 1e-140 && pm < 1e140);
-        cplx l = a[0] * rinv;
-        if (!(has && s > k)) l = cplx(0.0, 0.0);
-        if (real) lps[k] = l;
-        if (cand) Lg[(size_t) col * KL + (s - k - 1)] = l;            // zgbtf2 order
-        if (isrhs) sv[col] = l;                                       // y = b^T U^-1
-        if (pw == 0 && lane == 0) jpv[col] = 0;
+        for (int m = k + 1; m < P; ++m) pv[m] = shfl_c(a[m], k);
+        const double pm = __shfl_sync(0xffffffffu, mag, k);
+        const bool below = has && s > k;
+        cplx l = a[k] * rinv;
+        if (!below) l = cplx(0.0, 0.0);
 #pragma unroll
-        for (int m = 1; m < P; ++m) {
-            cplx t = a[m];
-            submul(t, l, pv[m]);
-            a[m - 1] = t;
-        }
+        for (int m = k + 1; m < P; ++m) submul(a[m], l, pv[m]);
+        // off the chain: izamax's rule, the published pivot row, the multipliers
+        bad |= below && mag > pm;
+        bad |= !(pm > 1e-140 && pm < 1e140);
+        sts_if(lp_sa + 16 * k, l, has);
+        st_global_if(Lrow + k * (KL - 1), l, below);                  // L(j+s, j+k) at Lcol[k (KL - 1) + s], zgbtf2 order
+        const bool piv = s == k;
+        sts_if(tr_sa + 16 * k, rs, piv);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}"
+                     :: "r"(tm_sa + 8 * k), "d"(mag), "r"((int) piv) : "memory");
+#pragma unroll
+        for (int m = k + 1; m < P; ++m) sts_if(tb_sa + 16 * (k * (9 - k) / 2 + m - k - 1), pv[m], piv);
     }
+    if (has) jpv[j + s] = 0;
     return __any_sync(0xffffffffu, bad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// F2(t), speculative: every other row of the panel (positions 5..RW-1 and the right-hand side), one
+// row per thread, no communication: l_k = a_k / u_kk, a_m -= l_k u_km with U11 and the reciprocal
+// pivots F1 published.  izamax's rule is checked on the side against the published pivot
+// magnitudes.  Returns this thread's verdict (true: redo the panel exactly).
+// ---------------------------------------------------------------------------------------------
+template <class W, class SM>
+__device__ __forceinline__ bool panel_rows(const SM &S, cplx *Lcol, cplx *sv, int j, int jr, int jc, int N, int t)
+{
+    constexpr int KL = W::KL, RW = W::RW, CW = W::CW;
+    const int s = P + t;                                   // row position
+    if (s > RW) return false;
+    const bool isrhs = s == RW;
+    int slot = RW;
+    if (s < RW) { slot = jr + s; if (slot >= RW) slot -= RW; }
+    const bool inmat = !isrhs && j + s < N;
+    cplx a[P];
+    {
+        const cplx *src = S.win + (size_t) slot * CW + jc;
+#pragma unroll
+        for (int m = 0; m < P; ++m) a[m] = src[m];
+    }
+    const unsigned lp_sa = smem_u32(S.lp + s * P);
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const bool cand = inmat && s <= k + KL;
+        bad |= cand && cabs1(a[k]) > S.tbm[k];
+        const cplx l = a[k] * S.tbr[k];
+#pragma unroll
+        for (int m = k + 1; m < P; ++m) submul(a[m], l, S.tbu[k * (9 - k) / 2 + m - k - 1]);
+        sts_if(lp_sa + 16 * k, l, true);
+        st_global_if(Lcol + (size_t) k * (KL - 1) + s, l, cand);
+        st_global_if(sv + j + k, l, isrhs);                // y = b^T U^-1
+    }
+    return bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// X(t): the pivot rows j+1..j+4 become rows of U in place (unit lower triangular solve with L11)
+// for one trailing column per thread.  The untouched values go to a global scratch (save != null)
+// so that a panel that turns out to need the exact path can be put back.
+// ---------------------------------------------------------------------------------------------
+template <class W, class SM>
+__device__ __forceinline__ void urows_column(const SM &S, int jr, int cs, cplx *save)
+{
+    constexpr int CW = W::CW;
+    cplx *pc = S.win + (size_t) jr * CW + cs;
+    cplx u[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) u[k] = pc[k * CW];
+    if (save) {
+#pragma unroll
+        for (int k = 1; k < P; ++k) save[(k - 1) * CW + cs] = u[k];
+    }
+#pragma unroll
+    for (int k = 1; k < P; ++k) {
+#pragma unroll
+        for (int i2 = 0; i2 < k; ++i2) submul(u[k], S.lp[k * P + i2], u[i2]);
+        pc[k * CW] = u[k];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,6 +412,7 @@ invert_sync_kernel(const PipeArgs A)
     unsigned char *const ipbase = IG ? A.ipwork + (size_t) blockIdx.x * 2 * N : S.ipiv;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
+    cplx *const xsave = A.xwork + (size_t) blockIdx.x * (P - 1) * CW;   // pivot rows as they were before a speculative X
 
     for (int t = tid; t < MAXTERMS; t += W::NTH) S.tref[t] = K.terms->ref[t];
     for (int t = tid; t <= NBLOCK; t += W::NTH) S.tblk[t] = K.terms->blk_begin[t];
@@ -373,39 +471,103 @@ invert_sync_kernel(const PipeArgs A)
         bar_sync_n<BAR_ALL>(NT);
 
         int info = 0, ju = 0, jr = 0, jc = 0;
+        double stg = 0.0;                                    // a staged global value on its way to shared memory
         SPROF_DECL
         for (int j = 0; j < N; j += P) {
-            const int yI = (j + RW) / P;                    // block row entering after this panel
-            // ---------------- F(t) | next coefficient point, operator rows ----------------
-            if (warp < W::NWP) {
-                const bool bad = panel_fast<W>(S, Lg, sv, jpv, j, jr, jc, N, lane, warp);
-                if (lane == 0) S.misc[8 + warp] = bad;
-                if (W::NWP == 1 && tid == 0) S.misc[9] = 0;
+            cplx *Lcol = Lg + (size_t) j * KL - 1;          // L(j + s, j + k) at Lcol[k (KL - 1) + s]
+            // ---------------- P1: F1(t) on the panel warp | A(t-1): the five rows entering after panel t-1
+            // replace its retired pivot rows; its column slots now stand for columns j-5+CW .. j-1+CW ----------------
+            if (warp == 0) {
+                const bool bad = panel_top<W>(S, Lcol, jpv, j, jr, jc, lane);
+                if (lane == 0) S.misc[8] = bad;
             } else {
-                constexpr int NTO = NT - 32 * W::NWP;
-                const int to = tid - 32 * W::NWP;
-                compute_coef_range<W>(K, S, yI + KB, 1, to, NTO);
-                for (int i = to; i < 3 * K.ld; i += NTO) {
-                    const int d = i / K.ld, r = i - d * K.ld, yJ = yI - r + K.ku;
-                    S.drow[i] = (yJ >= 0 && yJ < n) ? __ldg(K.D + (size_t) (d * K.ld + r) * n + yJ) : 0.0;
+                constexpr int NTA = NT - 32;
+                const int ta = tid - 32;
+                // global loads first, so that their latency hides behind the assembly: the reference-profile
+                // column of the coefficient point computed in P2 and the operator rows of the block row
+                // assembled in the next P1 (both consumed from shared memory)
+                const int tl = ta - (NTA - 96);                              // the last three warps do the loads
+                {
+                    const int yN = (j + RW) / P;                             // block row assembled in the next P1
+                    const int yc = yN + KB, i = tl - 32;
+                    if (tl >= 0 && tl <= SZB_NREF) stg = yc < n ? __ldg(K.refs + (size_t) tl * n + yc) : 0.0;
+                    if (i >= 0) {
+                        stg = 0.0;
+                        if (i < 3 * K.ld) {
+                            const int d = i / K.ld, r = i - d * K.ld, yJ = yN - r + K.ku;
+                            if (yJ >= 0 && yJ < n) stg = __ldg(K.D + (size_t) (d * K.ld + r) * n + yJ);
+                        }
+                    }
                 }
+              if (j > 0) {
+                const int yI = (j - P + RW) / P;
+                int jro = jr - P; if (jro < 0) jro += RW;
+                int jco = jc - P; if (jco < 0) jco += CW;
+                cplx *dst = S.win + (size_t) jro * CW;
+                if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
+                    assemble_block_interior<W>(K, S, S.drow, yI, dst, ta, NTA);
+                else
+                    assemble_block<W>(K, S, K.km[p], K.kn[p], yI, dst, ta, NTA);
+                for (int e = ta; e < (NS - P) * P; e += NTA) {
+                    const int sp = e / P, m = e - sp * P;                      // rows at positions 0..NS-P-1 of THIS panel
+                    int slot = RW;
+                    if (sp < RW - P) { slot = jr + sp; if (slot >= RW) slot -= RW; }
+                    cplx val(0.0, 0.0);
+                    if (sp == RW - P) { const int cn = j - P + CW + m; if (cn < N) val = ldcg_c(sv + cn); }
+                    S.win[(size_t) slot * CW + jco + m] = val;
+                }
+              }
+                if (tl >= 0 && tl <= SZB_NREF) S.refcol[tl] = stg;
             }
             SPROF_MARK(0);
             bar_sync_n<BAR_ALL>(NT);
             SPROF_MARK(1);
             SPROF_COUNT(7, 1);
+            // ---------------- P2: F2(t) rows | X(t) columns | next coefficient point, operator rows ----------------
             int juc = j + P - 1 + KU;
-            if (S.misc[8] | S.misc[9]) {
+            int ncols = min(max(ju, juc), N - 1) - (j + P) + 1;
+            constexpr int NW2 = (W::NR + 31) / 32;                            // warps of F2
+            constexpr int NWX = W::KV > 32 ? 2 : 1;                           // warps of X (KU trailing columns unless there is fill)
+            static_assert(NW2 + NWX < NWC, "warps left for the coefficient point");
+            bool mybad = false;
+            {
+                const int i = tid - (NT - 64);                                // staged operator rows (loaded in P1)
+                if (i >= 0 && i < 3 * K.ld) S.drow[i] = stg;
+            }
+            if (warp < NW2) {
+                mybad = panel_rows<W>(S, Lcol, sv, j, jr, jc, N, tid);
+            } else if (warp < NW2 + NWX) {
+                for (int i = tid - 32 * NW2; i < ncols; i += 32 * NWX) {
+                    int cs = jc + P + i; if (cs >= CW) cs -= CW;
+                    urows_column<W>(S, jr, cs, xsave);
+                }
+            } else {
+                constexpr int NTO = NT - 32 * (NW2 + NWX);
+                const int to = tid - 32 * (NW2 + NWX);
+                const int yI = (j + RW) / P;                                   // block row assembled in the next P1
+                compute_coef_staged<W>(K, S, yI + KB, S.refcol, to, NTO);
+            }
+            SPROF_MARK(2);
+            const int anybad = bar_red_or(mybad, NT);
+            SPROF_MARK(3);
+            if (anybad | S.misc[8]) {
                 SPROF_COUNT(6, 1);
+                // put the pivot rows back, redo the panel exactly, apply its interchanges, redo X
+                for (int c = tid; c < ncols; c += NT) {
+                    int cs = jc + P + c; if (cs >= CW) cs -= CW;
+#pragma unroll
+                    for (int k = 1; k < P; ++k) S.win[(size_t) (jr + k) * CW + cs] = ldcg_c(xsave + (k - 1) * CW + cs);
+                }
+                bar_sync_n<BAR_ALL>(NT);
                 if (warp < W::NWP) panel_slow<W>(S, Lg, sv, jpv, j, jr, jc, N, tid);
                 bar_sync_n<BAR_ALL>(NT);
                 info = S.misc[4];
                 if (info) break;
                 juc = S.misc[11];
+                ncols = min(max(ju, juc), N - 1) - (j + P) + 1;
                 if (S.misc[10]) {
                     // the panel's interchanges on the trailing columns, in order (zgbtf2's zswap to the right)
-                    const int ncs = min(max(ju, juc), N - 1) - (j + P) + 1;
-                    for (int c = tid; c < ncs; c += NT) {
+                    for (int c = tid; c < ncols; c += NT) {
                         int cs = jc + P + c; if (cs >= CW) cs -= CW;
 #pragma unroll
                         for (int k = 0; k < P; ++k) {
@@ -419,111 +581,85 @@ invert_sync_kernel(const PipeArgs A)
                     }
                     bar_sync_n<BAR_ALL>(NT);
                 }
+                for (int c = tid; c < ncols; c += NT) {
+                    int cs = jc + P + c; if (cs >= CW) cs -= CW;
+                    urows_column<W>(S, jr, cs, nullptr);
+                }
+                bar_sync_n<BAR_ALL>(NT);
             }
             ju = max(ju, juc);
-            SPROF_MARK(2);
-            // ---------------- X(t) + U(t): trailing columns j+5 .. ju, warp = columns, lane = row ----------------
+            // ---------------- P3: U(t): trailing columns j+5 .. ju, warp = columns (cyclically), lane = row.
+            // Column indices past the last one are pointed at the retired column slot jc: dead data.
+            // Explicit shared-memory addresses and loads in program order: every pivot-row operand is
+            // re-loaded right after its use, four complex updates ahead of the next one (the compiler's own
+            // schedule went column by column, a chain of ten dependent FMAs behind each load). ----------------
             {
-                const int ncols = min(ju, N - 1) - (j + P) + 1;
                 const int pos = P + lane;                                   // main rows: positions 5 .. 5 + NMAIN - 1
                 int rslot = RW;
                 if (pos < RW) { rslot = jr + pos; if (rslot >= RW) rslot -= RW; }
-                cplx l[P];
-                if (lane < W::NMAIN) {
-#pragma unroll
-                    for (int k = 0; k < P; ++k) l[k] = S.lp[pos * P + k];
-                }
-                const cplx *prow = S.win + (size_t) jr * CW;                // the five pivot rows
+                const unsigned lrow_sa = smem_u32(S.lp + (lane < W::NMAIN ? pos : P) * P);      // this lane's multipliers
+                const unsigned prow_sa = smem_u32(S.win + (size_t) jr * CW);    // the five pivot rows (rows of U now)
+                const unsigned dro = (unsigned) ((rslot - jr) * CW * (int) sizeof(cplx));   // this lane's row relative to them
+                constexpr unsigned ROWB = CW * sizeof(cplx);
                 for (int m0 = 0; warp + NWC * m0 < ncols; m0 += NCH) {
-                    // X: lanes 0..NCH-1, one column each
-                    if (lane < NCH) {
-                        const int i = warp + NWC * (m0 + lane);
-                        if (i < ncols) {
-                            int cs = jc + P + i; if (cs >= CW) cs -= CW;
-                            cplx u[P];
-#pragma unroll
-                            for (int k = 0; k < P; ++k) u[k] = prow[k * CW + cs];
-#pragma unroll
-                            for (int k = 1; k < P; ++k) {
-#pragma unroll
-                                for (int i2 = 0; i2 < k; ++i2) submul(u[k], S.lp[k * P + i2], u[i2]);
-                                S.win[(size_t) (jr + k) * CW + cs] = u[k];
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    int cs[NCH];
+                    unsigned ca[NCH];
 #pragma unroll
                     for (int x = 0; x < NCH; ++x) {
                         const int i = warp + NWC * (m0 + x);
                         int c = jc + P + i; if (c >= CW) c -= CW;
-                        cs[x] = i < ncols ? c : -1;
+                        ca[x] = prow_sa + 16u * (unsigned) (i < ncols ? c : jc);
                     }
                     if (lane < W::NMAIN) {
-                        cplx w[NCH];
-                        cplx *wrow = S.win + (size_t) rslot * CW;
+                        cplx w[NCH], u[NCH];
+                        cplx lk = lds_cv(lrow_sa);
 #pragma unroll
-                        for (int x = 0; x < NCH; ++x) w[x] = cs[x] >= 0 ? wrow[cs[x]] : cplx(0.0, 0.0);
+                        for (int x = 0; x < NCH; ++x) u[x] = lds_cv(ca[x]);
+#pragma unroll
+                        for (int x = 0; x < NCH; ++x) w[x] = lds_cv(ca[x] + dro);
 #pragma unroll
                         for (int k = 0; k < P; ++k) {
+                            cplx ln = lk;
+                            if (k + 1 < P) ln = lds_cv(lrow_sa + 16 * (k + 1));
 #pragma unroll
                             for (int x = 0; x < NCH; ++x) {
-                                const cplx uk = prow[k * CW + max(cs[x], 0)];
-                                submul(w[x], l[k], uk);
+                                submul(w[x], lk, u[x]);
+                                if (k + 1 < P) u[x] = lds_cv(ca[x] + (k + 1) * ROWB);
                             }
+                            lk = ln;
                         }
 #pragma unroll
-                        for (int x = 0; x < NCH; ++x) if (cs[x] >= 0) wrow[cs[x]] = w[x];
+                        for (int x = 0; x < NCH; ++x) sts_if(ca[x] + dro, w[x], true);
                     }
                     // tail rows (positions 5 + NMAIN .. RW): one element per lane
-                    if (W::NTAIL > 0) {
-                        for (int e = lane; e < W::NTAIL * NCH; e += 32) {
-                            const int x = e / W::NTAIL, r = e - x * W::NTAIL;
-                            const int i = warp + NWC * (m0 + x);
-                            if (i < ncols) {
-                                int c = jc + P + i; if (c >= CW) c -= CW;
-                                const int tp = P + W::NMAIN + r;
-                                int ts = RW;
-                                if (tp < RW) { ts = jr + tp; if (ts >= RW) ts -= RW; }
-                                cplx w = S.win[(size_t) ts * CW + c];
+                    for (int e = lane; e < W::NTAIL * NCH; e += 32) {
+                        const int x = e / (W::NTAIL > 0 ? W::NTAIL : 1), r = e - x * W::NTAIL;
+                        const int i = warp + NWC * (m0 + x);
+                        int c = jc + P + i; if (c >= CW) c -= CW;
+                        if (i >= ncols) c = jc;
+                        const int tp = P + W::NMAIN + r;
+                        int ts = RW;
+                        if (tp < RW) { ts = jr + tp; if (ts >= RW) ts -= RW; }
+                        const unsigned pu = prow_sa + 16u * (unsigned) c, pw = smem_u32(S.win + (size_t) ts * CW + c);
+                        const unsigned pl = smem_u32(S.lp + tp * P);
+                        cplx w = lds_c(pw), uu[P], ll[P];
 #pragma unroll
-                                for (int k = 0; k < P; ++k) submul(w, S.lp[tp * P + k], prow[k * CW + c]);
-                                S.win[(size_t) ts * CW + c] = w;
-                            }
-                        }
+                        for (int k = 0; k < P; ++k) { uu[k] = lds_c(pu + k * ROWB); ll[k] = lds_c(pl + 16 * k); }
+#pragma unroll
+                        for (int k = 0; k < P; ++k) submul(w, ll[k], uu[k]);
+                        sts_if(pw, w, true);
                     }
-                    __syncwarp();
                 }
             }
-            SPROF_MARK(3);
-            bar_sync_n<BAR_ALL>(NT);
             SPROF_MARK(4);
-            // ---------------- A(t): rows j+RW .. j+RW+4 replace the retired pivot rows; column slots
-            // jc .. jc+4 now stand for columns j+CW .. j+CW+4 ----------------
-            {
-                cplx *dst = S.win + (size_t) jr * CW;
-                if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
-                    assemble_block_interior<W>(K, S, S.drow, yI, dst, tid, NT);
-                else
-                    assemble_block<W>(K, S, km, kn, yI, dst, tid, NT);
-                for (int e = tid; e < (NS - P) * P; e += NT) {
-                    const int sp = e / P, m = e - sp * P, pos = P + sp;
-                    int slot = RW;
-                    if (pos < RW) { slot = jr + pos; if (slot >= RW) slot -= RW; }
-                    cplx val(0.0, 0.0);
-                    if (pos == RW) { const int cn = j + CW + m; if (cn < N) val = ldcg_c(sv + cn); }
-                    S.win[(size_t) slot * CW + jc + m] = val;
-                }
-            }
-            SPROF_MARK(5);
             bar_sync_n<BAR_ALL>(NT);
-            SPROF_MARK(1);
+            SPROF_MARK(5);
             jr += P; if (jr >= RW) jr -= RW;
             jc += P; if (jc >= CW) jc -= CW;
         }
 #ifdef SZB_PIPE_PROF
         if (tid == 0) SPROF_FLUSH(0);
-        if (tid == 32 * W::NWP) SPROF_FLUSH(8);
+        if (tid == 64) SPROF_FLUSH(8);
+        if (tid == 160) SPROF_FLUSH(16);
 #endif
         if (tid == 0) { S.misc[buf] = info; if (info) for (int k = 0; k < N; ++k) jpv[k] = 0; }
         __threadfence();
@@ -554,7 +690,8 @@ int launch_sync_ig(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t 
     const size_t lbytes = (size_t) slots * 2 * ((((size_t) N * W::KL) + 7) & ~(size_t) 7) * sizeof(cplx);
     const size_t vbytes = (size_t) slots * 2 * N * sizeof(cplx);
     const size_t ibytes = IG ? (((size_t) slots * 2 * N + 255) & ~(size_t) 255) : 0;
-    const size_t need = lbytes + vbytes + ibytes;
+    const size_t xbytes = (size_t) slots * (P - 1) * W::CW * sizeof(cplx);
+    const size_t need = lbytes + vbytes + xbytes + ibytes;
     if (need > op->work_bytes) {
         if (op->d_work) SZB_CUDA_OK(cudaFree(op->d_work));
         op->d_work = nullptr; op->work_bytes = 0;
@@ -565,7 +702,8 @@ int launch_sync_ig(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t 
     unsigned char *w = static_cast<unsigned char *>(op->d_work);
     A.lwork = reinterpret_cast<cplx *>(w);
     A.vwork = reinterpret_cast<cplx *>(w + lbytes);
-    A.ipwork = IG ? w + lbytes + vbytes : nullptr;
+    A.xwork = reinterpret_cast<cplx *>(w + lbytes + vbytes);
+    A.ipwork = IG ? w + lbytes + vbytes + xbytes : nullptr;
     invert_sync_kernel<W, IG><<<slots, W::NTH, smem, stream>>>(A);
     count_launch();
     SZB_CUDA_OK(cudaGetLastError());
@@ -598,7 +736,7 @@ int invert_sync_dispatch(const szb_imexop *op, const double phi[2], int npencil,
     A.npencil = npencil; A.index = d_index;
     A.state = d_state; A.fs = fs; A.ps = ps;
     A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
-    A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr;
+    A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr; A.xwork = nullptr;
     A.zero_wall_rhs = zero_wall_rhs;
     if (op->A.KL != op->A.KU) return 1;
     switch (op->A.KL) {
@@ -613,14 +751,14 @@ int invert_sync_dispatch(const szb_imexop *op, const double phi[2], int npencil,
 }  // namespace szb
 
 // debug hook (not part of the C ABI): phase clocks accumulated by a PROF=1 build
-extern "C" int szb_debug_sync_prof(unsigned long long out[16], int reset)
+extern "C" int szb_debug_sync_prof(unsigned long long out[24], int reset)
 {
 #ifdef SZB_PIPE_PROF
-    if (cudaMemcpyFromSymbol(out, g_sync_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_sync_prof, z, sizeof z); }
+    if (cudaMemcpyFromSymbol(out, g_sync_prof, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(g_sync_prof, z, sizeof z); }
     return 1;
 #else
-    for (int i = 0; i < 16; ++i) out[i] = 0;
+    for (int i = 0; i < 24; ++i) out[i] = 0;
     (void) reset;
     return 0;
 #endif

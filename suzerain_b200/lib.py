@@ -97,6 +97,7 @@ PROTOTYPES = {
     "szb_imexop_destroy": (None, [c_void_p]),
     "szb_imexop_set_scenario": (C.c_int, [c_void_p, C.POINTER(Scenario)]),
     "szb_imexop_set_refs": (C.c_int, [c_void_p, C.POINTER(Ref), C.POINTER(RefLd)]),
+    "szb_imexop_set_refs_device": (C.c_int, [c_void_p, c_void_p, C.c_int, c_void_p]),
     "szb_imexop_set_isothermal": (C.c_int, [c_void_p, C.POINTER(Isothermal)]),
     "szb_imexop_set_nrbc": (C.c_int, [c_void_p, c_double_p, c_double_p, c_double_p]),
     "szb_imexop_bsmbsm": (Bsmbsm, [c_void_p]),

@@ -19,7 +19,7 @@ km = torch.from_numpy(case.km).to(dev); kn = torch.from_numpy(case.kn).to(dev)
 x0 = torch.from_numpy(case.x.copy()).to(dev)
 info = torch.zeros(len(case.km), dtype=torch.int32, device=dev)
 lib = L.load()
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 24)()
 spec = sz.SolverSpec(method="zgbsv")
 st = x0.clone(); op.invert_batch(spec, case.phi, km, kn, st, info=info); torch.cuda.synchronize()
 has = hasattr(lib, "szb_debug_sync_prof") and lib.szb_debug_sync_prof(buf, 1) == 1
@@ -30,8 +30,7 @@ print(f"{cfg} {len(case.km)} pencils: invert {t0.elapsed_time(t1):.3f} ms, info 
 if has and lib.szb_debug_sync_prof(buf, 1) == 1:
     v = list(buf)
     npanel = max(v[7], 1)
-    names = ["F", "wait B1+B3", "exact+swap", "X/U", "wait B2", "A"]
     print("panels", v[7], "exact-path panels", v[6], f"({100.0 * v[6] / npanel:.1f} %)")
-    print("panel warp 0   :", {k: round(v[i] / npanel) for i, k in enumerate(names)}, "sum", round(sum(v[:6]) / npanel))
-    names = ["coef+rows", "wait B1+B3", "exact+swap", "X/U", "wait B2", "A"]
-    print("non-panel warp :", {k: round(v[8 + i] / npanel) for i, k in enumerate(names)}, "sum", round(sum(v[8:14]) / npanel))
+    names = ["P1 work", "B1 wait", "P2 work", "B2 wait", "P3 work", "B3 wait"]
+    for base, who in ((0, "warp 0 (F1 | F2 | U)"), (8, "warp 2 (A  | X  | U)"), (16, "warp 5 (A  | coef | U)")):
+        print(f"{who:24s}:", {k: round(v[base + i] / npanel) for i, k in enumerate(names)}, "sum", round(sum(v[base:base + 6]) / npanel))
