@@ -239,6 +239,13 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
 /* Bytes of device scratch the batched invert holds (for capacity planning). */
 size_t szb_imexop_workspace_bytes(const szb_imexop *op);
 
+/* a <-> b for the listed pencils (null: all) of two device states in different layouts: the
+ * exchange of an interleaved_state with a contiguous_state that lowstorage::step performs after
+ * every accumulate (suzerain/lowstorage.hpp:1511, suzerain/state.hpp:486-520,607-630). */
+int szb_state_exchange(int npencil, const int *d_index, int S, int n,
+                       szb_complex *d_a, size_t a_field_stride, size_t a_pencil_stride,
+                       szb_complex *d_b, size_t b_field_stride, size_t b_pencil_stride, void *stream);
+
 /* Zero-fill the listed pencils (dealiased / Nyquist modes,
  * operator_hybrid_isothermal.cpp:632-637). */
 int szb_zero_pencils(int npencil, const int *d_index, int S, int n,

@@ -464,6 +464,14 @@ class OperatorHybridIsothermalDevice:
                                         y_strides=None if interleaved_output else (n * self.npencil, n),
                                         stream=stream)
 
+    def exchange(self, a, b, stream=None):
+        """a <-> b between the interleaved state a (npencil, 5, Ny) and the contiguous state b (5, npencil, Ny):
+        `b.exchange(a)` of lowstorage::step (suzerain/lowstorage.hpp:1511), every stored pencil."""
+        n = self.op.n
+        rc = _L.load().szb_state_exchange(self.npencil, None, 5, n, _ptr(a), n, 5 * n,
+                                          _ptr(b), n * self.npencil, n, _stream_handle(stream))
+        _L.check("szb_state_exchange", rc)
+
     def invert_mass_plus_scaled_operator(self, phi, state, stream=None, ipiv=None, iters=None):
         n = self.op.n
         if len(self.h_inactive):

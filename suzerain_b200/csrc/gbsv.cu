@@ -575,6 +575,43 @@ int szb_zero_pencils(int npencil, const int *d_index, int S, int n, szb_complex 
     return 0;
 }
 
+// a <-> b between two state layouts (suzerain/state.hpp:486-520,607-630: exchange of an
+// interleaved_state with a contiguous_state as lowstorage::step does after every accumulate,
+// suzerain/lowstorage.hpp:1511): one CTA per pencil, whole wall-normal lines of both states.
+__global__ void state_exchange_kernel(int npencil, const int *index, int S, int n, cplx *a, size_t afs, size_t aps,
+                                      cplx *b, size_t bfs, size_t bps)
+{
+    for (int q = blockIdx.x; q < npencil; q += gridDim.x) {
+        const size_t p = index ? (size_t) index[q] : (size_t) q;
+        cplx *va = a + p * aps, *vb = b + p * bps;
+        for (int e = threadIdx.x; e < S * n; e += blockDim.x) {
+            const int f = e / n, y = e - f * n;
+            const cplx x = va[(size_t) f * afs + y], z = vb[(size_t) f * bfs + y];
+            va[(size_t) f * afs + y] = z; vb[(size_t) f * bfs + y] = x;
+        }
+    }
+}
+
+int szb_state_exchange(int npencil, const int *d_index, int S, int n,
+                       szb_complex *d_a, size_t a_field_stride, size_t a_pencil_stride,
+                       szb_complex *d_b, size_t b_field_stride, size_t b_pencil_stride, void *stream)
+{
+    if (npencil < 0) return -1;
+    if (S < 0) return -3;
+    if (n < 0) return -4;
+    if (!d_a) return -5;
+    if (!d_b) return -8;
+    if (d_a == d_b) return -8;
+    if (npencil == 0) return 0;
+    const int grid = npencil < 148 * 16 ? npencil : 148 * 16;
+    state_exchange_kernel<<<grid, 128, 0, (cudaStream_t) stream>>>(npencil, d_index, S, n,
+        reinterpret_cast<cplx *>(d_a), a_field_stride, a_pencil_stride,
+        reinterpret_cast<cplx *>(d_b), b_field_stride, b_pencil_stride);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static size_t invert_slot_bytes(const szb_imexop *op, int method)
 {
     const size_t N = op->A.N, ldlu = op->A.LD + op->A.KL;
@@ -590,7 +627,7 @@ namespace szb {
 int invert_fused_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                           const double *d_km, const double *d_kn, const int *d_index,
                           cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                          int *d_iters, cudaStream_t stream, int zero_wall_rhs)
+                          int *d_iters, cudaStream_t stream, int zero_wall_rhs, const int *d_count)
 {
     static const int which = [] {
         const char *e = std::getenv("SZB_INVERT");
@@ -599,10 +636,10 @@ int invert_fused_dispatch(const szb_imexop *op, const double phi[2], int npencil
     int rc = 1;
     if (which == 5)
         rc = invert_sync_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info, d_iters,
-                                  stream, zero_wall_rhs);
+                                  stream, zero_wall_rhs, d_count);
     if (rc == 1)
         rc = invert_pipe_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info, d_iters,
-                                  stream, zero_wall_rhs);
+                                  stream, zero_wall_rhs, d_count);
     return rc;
 }
 }  // namespace szb

@@ -90,6 +90,7 @@ struct AccumulateArgs {
     int nrbc;               // bit0 a, bit1 b, bit2 c
     double a[25], b[25], c[25];
     int npencil;
+    const int *count_dev;   // optional device-side pencil count (<= npencil)
     int zero_wave;          // linearize::rhome_y: the operator at km = kn = 0 for every pencil
     const int *index_out;   // slot of the output pencil when it differs from the input's (null: the same ...
     int out_plain;          // ... or, with this flag, the pencil's own number)
@@ -155,16 +156,17 @@ accumulate_kernel(const AccumulateArgs A)
         for (int f = 0; f < 5; ++f)
             fused::tma_bulk_g2s(s_inbuf + (stage * 5 + f) * np + ku, src + (size_t) f * A.in_fs, bytes, &s_mbar[stage]);
     };
-    if (threadIdx.x == 0 && (int) blockIdx.x < A.npencil) fetch(blockIdx.x, 0);
+    const int npen = A.count_dev ? min(A.npencil, __ldg(A.count_dev)) : A.npencil;
+    if (threadIdx.x == 0 && (int) blockIdx.x < npen) fetch(blockIdx.x, 0);
     const int nterms = A.terms->nterms;
     int it = 0;
-    for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++it) {
+    for (int p = blockIdx.x; p < npen; p += gridDim.x, ++it) {
     const int stage = it & 1;
     const cplx *s_in = s_inbuf + stage * 5 * np;
     const double km = A.zero_wave ? 0.0 : A.km[p], kn = A.zero_wave ? 0.0 : A.kn[p];
     const size_t slot = A.index ? (size_t) A.index[p] : (size_t) p;
     cplx *out = A.out + (A.index_out ? (size_t) A.index_out[p] : A.out_plain ? (size_t) p : slot) * A.out_ps;
-    if (threadIdx.x == 0 && p + (int) gridDim.x < A.npencil) fetch(p + gridDim.x, stage ^ 1);
+    if (threadIdx.x == 0 && p + (int) gridDim.x < npen) fetch(p + gridDim.x, stage ^ 1);
     for (int t = threadIdx.x; t < nterms; t += blockDim.x)
         s_alpha[t] = A.phi * (wave_factor(A.terms->wave[t], km, kn) * A.terms->sc[t]);
     fused::mbar_wait(&s_mbar[stage], (it >> 1) & 1);
@@ -261,7 +263,7 @@ int accumulate_launch(const szb_imexop *op, const double phi[2],
         int npencil, const double *d_km, const double *d_kn, const int *d_index, const int *d_index_out, int out_plain,
         const szb_complex *d_in, size_t in_fs, size_t in_ps,
         const double beta[2],
-        szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream)
+        szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream, const int *d_count)
 {
     if (!op) return -1;
     if (!phi) return -2;
@@ -285,7 +287,7 @@ int accumulate_launch(const szb_imexop *op, const double phi[2],
     std::memcpy(A.a, op->nrbc_a, sizeof(A.a));
     std::memcpy(A.b, op->nrbc_b, sizeof(A.b));
     std::memcpy(A.c, op->nrbc_c, sizeof(A.c));
-    A.npencil = npencil;
+    A.npencil = npencil; A.count_dev = d_count;
     A.zero_wave = op->linearization == SZB_LINEARIZE_RHOME_Y;
     const size_t smem = sizeof(cplx) * (10 * (size_t) (op->n + op->kl + op->ku) + MAXTERMS + 8);
     if (smem > 227 * 1024) return -1;

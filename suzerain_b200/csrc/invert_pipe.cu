@@ -345,7 +345,8 @@ invert_pipe_kernel(const PipeArgs A)
     constexpr int ROLE_UPDATE = 0, ROLE_ASSEMBLE = 1, ROLE_PANEL = 2;
     const int role = warp < W::NWU ? ROLE_UPDATE : warp < W::NWU + W::NWA ? ROLE_ASSEMBLE : ROLE_PANEL;
     int q = 0;
-    for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
+    const int npen = A.count_dev ? min(A.npencil, __ldg(A.count_dev)) : A.npencil;
+    for (int p = blockIdx.x; p < npen; p += gridDim.x, ++q) {
         const int buf = q & 1;
         if (q >= 2) { if (buf == 0) bar_sync_n<BAR_EMPTY0>(W::NTH); else bar_sync_n<BAR_EMPTY1>(W::NTH); }
         cplx *sv = vbase + (size_t) buf * N;
@@ -771,6 +772,7 @@ int launch_pipe(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t str
 struct ResidualArgs {
     PackArgs pk;                    // km / kn indexed by pencil
     int nlist; const int *pos;      // pencils to process (null: all npencil)
+    const int *count_dev;           // optional device-side length of the list (<= nlist)
     const int *index;               // pencil -> slot of the state
     cplx *x; size_t fs, ps;         // solution, state layout
     const cplx *b;                  // [npencil][5][n] right hand sides (wall rows still to be zeroed)
@@ -806,7 +808,8 @@ residual_kernel(const ResidualArgs A)
     for (int t = tid; t < MAXTERMS; t += 256) S.tref[t] = K.terms->ref[t];
     for (int t = tid; t <= NBLOCK; t += 256) S.tblk[t] = K.terms->blk_begin[t];
     __syncthreads();
-    for (int e = blockIdx.x; e < A.nlist; e += gridDim.x) {
+    const int nlist = A.count_dev ? min(A.nlist, __ldg(A.count_dev)) : A.nlist;
+    for (int e = blockIdx.x; e < nlist; e += gridDim.x) {
         const int p = A.pos ? A.pos[e] : e;
         const double km = K.km[p], kn = K.kn[p];
         cplx *x = A.x + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
@@ -916,7 +919,8 @@ residual_fix_kernel(const ResidualArgs A)
     for (int t = tid; t < MAXTERMS; t += 128) S.tref[t] = K.terms->ref[t];
     for (int t = tid; t <= NBLOCK; t += 128) S.tblk[t] = K.terms->blk_begin[t];
     __syncthreads();
-    for (int e = blockIdx.x; e < A.nlist; e += gridDim.x) {
+    const int nlist = A.count_dev ? min(A.nlist, __ldg(A.count_dev)) : A.nlist;
+    for (int e = blockIdx.x; e < nlist; e += gridDim.x) {
         const int p = A.pos ? A.pos[e] : e;
         const double km = K.km[p], kn = K.kn[p];
         const cplx *x = A.x + (A.index ? (size_t) A.index[p] : (size_t) p) * A.ps;
@@ -971,9 +975,10 @@ residual_fix_kernel(const ResidualArgs A)
 }
 
 // x += d for the pencils that go on, and their R <- b for the next accumulate
-__global__ void refine_update_kernel(int nlist, const int *pos, int N, int n, const int *index, cplx *x, size_t fs, size_t ps,
+__global__ void refine_update_kernel(int nlist, const int *count_dev, const int *pos, int N, int n, const int *index, cplx *x, size_t fs, size_t ps,
                                      const cplx *b, cplx *r, int add)
 {
+    if (count_dev && (int) blockIdx.x >= __ldg(count_dev)) return;
     const int p = pos ? pos[blockIdx.x] : blockIdx.x;
     cplx *xv = x + (index ? (size_t) index[p] : (size_t) p) * ps;
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
@@ -1076,11 +1081,11 @@ int dispatch_residual_fix(const szb_imexop *op, ResidualArgs &A, cudaStream_t st
 int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                         int *d_iters, cudaStream_t stream, int zero_wall_rhs)
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs, const int *d_count)
 {
     PipeArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
-    A.npencil = npencil; A.index = d_index;
+    A.npencil = npencil; A.index = d_index; A.count_dev = d_count;
     A.state = d_state; A.fs = fs; A.ps = ps;
     A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
     A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr; A.xwork = nullptr;
@@ -1155,34 +1160,34 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
     static const bool via_accumulate = [] { const char *e = std::getenv("SZB_REFINE_ACC"); return !(e && e[0] == '0'); }();
     const bool acc = via_accumulate && mode == 0 && op->A.KL == op->A.KU
                      && (op->A.KL == 14 || op->A.KL == 24 || op->A.KL == 34 || op->A.KL == 44);
-    auto residual = [&](int nlist, const int *list, const double *kml, const double *knl, const int *slot_in, int add, int it) -> int {
-        A.nlist = nlist; A.pos = list; A.add = add; A.it = it;
+    // No host synchronisation: the list of pencils that go on lives on the device together with its length
+    // (count), which the kernels of a refinement step read themselves; the host enqueues all dmax steps, the
+    // ones past the last active pencil find an empty list and return at once (~5 us per launch).
+    auto residual = [&](int nlist, const int *cnt, const int *list, const double *kml, const double *knl,
+                        const int *slot_in, int add, int it) -> int {
+        A.nlist = nlist; A.count_dev = cnt; A.pos = list; A.add = add; A.it = it;
         if (!acc) return dispatch_residual(op, A, stream);
         if (nlist < 1) return 0;
         // x += d and R <- b for the listed pencils, R <- (M + phi L) x - R, then walls / sign / norm / stopping rule
-        refine_update_kernel<<<nlist, 128, 0, stream>>>(nlist, list, N, n, d_index, d_state, fs, ps, B, R, add);
+        refine_update_kernel<<<nlist, 128, 0, stream>>>(nlist, cnt, list, N, n, d_index, d_state, fs, ps, B, R, add);
         count_launch();
         const double minus_one[2] = { -1.0, 0.0 };
         int rc2 = accumulate_launch(op, phi, nlist, kml, knl, slot_in, list, 1, reinterpret_cast<const szb_complex *>(d_state),
-                                    fs, ps, minus_one, reinterpret_cast<szb_complex *>(R), (size_t) n, (size_t) N, stream);
+                                    fs, ps, minus_one, reinterpret_cast<szb_complex *>(R), (size_t) n, (size_t) N, stream, cnt);
         if (rc2) return rc2;
         return dispatch_residual_fix(op, A, stream);
     };
-    if ((rc = residual(npencil, nullptr, d_km, d_kn, d_index, 0, 0))) return rc;
+    if ((rc = residual(npencil, nullptr, nullptr, d_km, d_kn, d_index, 0, 0))) return rc;
     for (int it = 1; it <= dmax; ++it) {
         SZB_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int), stream));
         refine_compact_kernel<<<(npencil + 255) / 256, 256, 0, stream>>>(npencil, cont, d_info, d_km, d_kn,
                                                                          pos, kma, kna, count, d_index, acc ? slot2 : nullptr);
         count_launch();
-        int nact = 0;
-        SZB_CUDA_OK(cudaMemcpyAsync(&nact, count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        SZB_CUDA_OK(cudaStreamSynchronize(stream));
-        if (nact == 0) break;
         // d = (LU)^-T r, in place in R (compact layout: field stride n, pencil stride N)
-        rc = invert_fused_dispatch(op, phi, nact, kma, kna, pos, R, (size_t) n, (size_t) N, nullptr, info2,
-                                   nullptr, stream, 0);
+        rc = invert_fused_dispatch(op, phi, npencil, kma, kna, pos, R, (size_t) n, (size_t) N, nullptr, info2,
+                                   nullptr, stream, 0, count);
         if (rc) return rc;
-        if ((rc = residual(nact, pos, kma, kna, slot2, 1, it))) return rc;
+        if ((rc = residual(npencil, count, pos, kma, kna, slot2, 1, it))) return rc;
     }
     refine_finish_kernel<<<(npencil + 255) / 256, 256, 0, stream>>>(npencil, d_info, diter, d_iters);
     count_launch();

@@ -431,7 +431,8 @@ invert_sync_kernel(const PipeArgs A)
     // ============================ compute warps ============================
     const int lane = tid & 31, warp = tid >> 5;
     int q = 0;
-    for (int p = blockIdx.x; p < A.npencil; p += gridDim.x, ++q) {
+    const int npen = A.count_dev ? min(A.npencil, __ldg(A.count_dev)) : A.npencil;
+    for (int p = blockIdx.x; p < npen; p += gridDim.x, ++q) {
         const int buf = q & 1;
         if (q >= 2) { if (buf == 0) bar_sync_n<BAR_EMPTY0>(W::NTH); else bar_sync_n<BAR_EMPTY1>(W::NTH); }
         cplx *sv = vbase + (size_t) buf * N;
@@ -729,11 +730,11 @@ int launch_sync(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t str
 int invert_sync_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                         int *d_iters, cudaStream_t stream, int zero_wall_rhs)
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs, const int *d_count)
 {
     PipeArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
-    A.npencil = npencil; A.index = d_index;
+    A.npencil = npencil; A.index = d_index; A.count_dev = d_count;
     A.state = d_state; A.fs = fs; A.ps = ps;
     A.ipiv_out = d_ipiv; A.info_out = d_info; A.iters_out = d_iters;
     A.lwork = nullptr; A.vwork = nullptr; A.ipwork = nullptr; A.xwork = nullptr;

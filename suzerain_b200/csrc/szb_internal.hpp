@@ -27,20 +27,22 @@ void field_ctx_free(void *p);      // capi.cu: cached whole-field plan of an ope
 struct cplx;
 int accumulate_launch(const szb_imexop *op, const double phi[2], int npencil, const double *d_km, const double *d_kn,
                       const int *d_index, const int *d_index_out, int out_plain, const szb_complex *d_in, size_t in_fs, size_t in_ps,
-                      const double beta[2], szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream);
+                      const double beta[2], szb_complex *d_out, size_t out_fs, size_t out_ps, void *stream,
+                      const int *d_count = nullptr);
 int invert_pipe_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                         int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1, const int *d_count = nullptr);
 int invert_sync_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                          const double *d_km, const double *d_kn, const int *d_index,
                          cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                         int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
+                         int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1, const int *d_count = nullptr);
 // the fused zgbsv kernel in use: v5 (invert_sync.cu) unless SZB_INVERT=v4 or v5 has no instantiation
+// d_count: optional device-side pencil count (<= npencil), read by the kernel instead of a host sync
 int invert_fused_dispatch(const szb_imexop *op, const double phi[2], int npencil,
                           const double *d_km, const double *d_kn, const int *d_index,
                           cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
-                          int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1);
+                          int *d_iters, cudaStream_t stream, int zero_wall_rhs = 1, const int *d_count = nullptr);
 int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,

@@ -1,0 +1,317 @@
+"""Round-2 GPU parity tests: entry points that were exported but unverified (szb_zcgbsvx_batch,
+szb_zgbtrs_batch('T'), general alpha/beta of zaPxpby, szb_state_exchange,
+szb_imexop_set_refs_device), the (kx,kz)-sharded substep on real device shards against the
+single-rank result, larger wavenumber samples of the two big BASELINE grids, and a long run on
+the bench grid under both solvers.  Every test calls through the C ABI and compares with oracle/
+(the reference's own C built into oracle/_ref, or LAPACK from SciPy's OpenBLAS)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity_common as pc                                    # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _band_systems(case, nsys, with_bc=True):
+    """P (M + phi L)^T P^T of the first nsys pencils in LAPACK band storage (LD rows, packc) from the
+    reference's own assembly."""
+    mats = [pc.oracle_assemble(case, p, packf=False, with_bc=with_bc) for p in range(nsys)]
+    return np.stack(mats)                                      # (nsys, N, LD)
+
+
+# ---------------------------------------------------------------------------
+# bsmbsm_solver protocol on pre-assembled matrices
+# ---------------------------------------------------------------------------
+def test_zgbtrs_batch_transposed_matches_lapack(dev):
+    """szb_zgbtrf_batch + szb_zgbtrs_batch('T') -- the only mode the reference uses
+    (bsmbsm_solver.cpp:171-179) -- against the reference's own suzerain_lapack_zgbtrf/zgbtrs('T')."""
+    import torch
+    from suzerain_b200 import lib as L
+    from oracle import ref as oref
+    case = pc.make_case("tiny_16x24x16", max_pencils=12)
+    nsys = len(case.km)
+    papt = _band_systems(case, nsys)
+    N, LD = papt.shape[1], papt.shape[2]
+    KL = KU = (LD - 1) // 2
+    ld = 2 * KL + KU + 1
+    ab = np.zeros((nsys, N, ld), dtype=np.complex128)
+    ab[:, :, KL:] = papt
+    rng = np.random.default_rng(7)
+    nrhs = 3
+    B = rng.standard_normal((nsys, nrhs, N)) + 1j * rng.standard_normal((nsys, nrhs, N))
+    lib = L.load()
+    d_ab = torch.from_numpy(ab.copy()).to(dev)
+    d_b = torch.from_numpy(B.copy()).to(dev)
+    ipiv = torch.zeros((nsys, N), dtype=torch.int32, device=dev)
+    info = torch.full((nsys,), -1, dtype=torch.int32, device=dev)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check("zgbtrf", lib.szb_zgbtrf_batch(N, KL, KU, _p(d_ab), ld, N * ld, _p(ipiv), _p(info), nsys, s))
+    L.check("zgbtrs", lib.szb_zgbtrs_batch(b"T", N, KL, KU, nrhs, _p(d_ab), ld, N * ld, _p(ipiv), _p(d_b), N,
+                                           nrhs * N, nsys, s))
+    torch.cuda.synchronize()
+    assert np.all(info.cpu().numpy() == 0)
+    got = d_b.cpu().numpy()
+    for i in range(nsys):
+        _, piv, X, rinfo = oref.zgbsv_T(N, KL, KU, ab[i], B[i])
+        assert rinfo == 0
+        assert pc.relmax(got[i], X) <= TOL
+        assert np.array_equal(ipiv[i].cpu().numpy(), piv)
+
+
+def test_zcgbsvx_batch_matches_reference_lapackext(dev):
+    """szb_zcgbsvx_batch against the reference's own suzerain_lapackext_zcgbsvx
+    (suzerain/blas_et_al/dsgbsvx.def:71-318) with the default specification (fact = 'N', siter < 0,
+    aiter = 1, diter = 5, tolsc = 0), TRANS = 'T' and 'N': solution, iteration count, residual."""
+    import torch
+    from suzerain_b200 import lib as L
+    from oracle import ref as oref
+    case = pc.make_case("tiny_16x24x16", max_pencils=10)
+    nsys = len(case.km)
+    papt = _band_systems(case, nsys)
+    N, LD = papt.shape[1], papt.shape[2]
+    KL = KU = (LD - 1) // 2
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((nsys, N)) + 1j * rng.standard_normal((nsys, N))
+    lib = L.load()
+    rl = oref.lib()
+    f = rl.suzerain_lapackext_zcgbsvx
+    f.restype = C.c_int
+    for trans in (b"T", b"N"):
+        d_ab = torch.from_numpy(papt.copy()).to(dev)
+        d_afb = torch.zeros((nsys, N, 2 * KL + KU + 1), dtype=torch.complex128, device=dev)
+        d_b = torch.from_numpy(B.copy()).to(dev)
+        d_x = torch.zeros_like(d_b)
+        ipiv = torch.zeros((nsys, N), dtype=torch.int32, device=dev)
+        iters = torch.zeros((nsys,), dtype=torch.int32, device=dev)
+        res = torch.zeros((nsys,), dtype=torch.float64, device=dev)
+        info = torch.full((nsys,), -1, dtype=torch.int32, device=dev)
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = lib.szb_zcgbsvx_batch(trans, N, KL, KU, 1, 5, C.c_double(0.0), _p(d_ab), N * LD, _p(d_afb),
+                                   N * (2 * KL + KU + 1), _p(ipiv), _p(d_b), _p(d_x), _p(iters), _p(res), _p(info),
+                                   nsys, s)
+        L.check("szb_zcgbsvx_batch", rc)
+        torch.cuda.synchronize()
+        assert np.all(info.cpu().numpy() == 0)
+        got, git, gres = d_x.cpu().numpy(), iters.cpu().numpy(), res.cpu().numpy()
+        for i in range(nsys):
+            ab = np.ascontiguousarray(papt[i])
+            afb = np.zeros((N, 2 * KL + KU + 1), dtype=np.complex128)
+            piv = np.zeros(N, dtype=np.int32)
+            b = B[i].copy(); x = np.zeros(N, dtype=np.complex128); r = np.zeros(N, dtype=np.complex128)
+            fact = C.c_char(b"N"); apprx = C.c_int(0); siter = C.c_int(-1); diter = C.c_int(5)
+            tolsc = C.c_double(0.0); afrob = C.c_double(-1.0); rres = C.c_double(0.0)
+            pp = lambda a: a.ctypes.data_as(C.c_void_p)
+            rc2 = f(C.byref(fact), C.byref(apprx), C.c_int(1), C.c_char(trans), C.c_int(N), C.c_int(KL), C.c_int(KU),
+                    pp(ab), C.byref(afrob), pp(afb), pp(piv), pp(b), pp(x), C.byref(siter), C.byref(diter),
+                    C.byref(tolsc), pp(r), C.byref(rres))
+            assert rc2 == 0
+            assert pc.relmax(got[i], x) <= TOL
+            assert abs(int(git[i]) - diter.value) <= 1              # stagnation may be seen one step apart
+            assert gres[i] <= 10 * max(rres.value, 1e-16 * np.abs(B[i]).max() * np.sqrt(N))
+            assert np.array_equal(ipiv[i].cpu().numpy(), piv)
+
+
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (0.5 - 2j, 0.0), (1.0, 1.0), (-1.0, 0.25j), (2.5 + 1j, -0.75 + 0.5j),
+                                        (0.0, 1.0)])
+@pytest.mark.parametrize("trans", ["N", "T"])
+def test_zaPxpby_general_alpha_beta(dev, alpha, beta, trans):
+    """suzerain_bsmbsm_zaPxpby (bsmbsm_aPxpby_complex.def:37-336) for general scalars, against the
+    permutation written out: y[k] <- alpha x[q(k)] + beta y[k] ('N'), q and qinv swapped for 'T'."""
+    import torch
+    from suzerain_b200 import lib as L
+    S, n, nb = 5, 9, 4
+    N = S * n
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((nb, N)) + 1j * rng.standard_normal((nb, N))
+    y = rng.standard_normal((nb, N)) + 1j * rng.standard_normal((nb, N))
+    lib = L.load()
+    q = np.array([lib.szb_bsmbsm_q(S, n, i) for i in range(N)])
+    qinv = np.array([lib.szb_bsmbsm_qinv(S, n, i) for i in range(N)])
+    perm = q if trans == "N" else qinv
+    want = alpha * x[:, perm] + beta * y
+    dx, dy = torch.from_numpy(x.copy()).to(dev), torch.from_numpy(y.copy()).to(dev)
+    d2 = lambda z: (C.c_double * 2)(complex(z).real, complex(z).imag)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check("zaPxpby", lib.szb_bsmbsm_zaPxpby_batch(trans.encode(), S, n, d2(alpha), _p(dx), d2(beta), _p(dy), nb, s))
+    torch.cuda.synchronize()
+    assert np.abs(dy.cpu().numpy() - want).max() <= 4 * np.finfo(float).eps * max(np.abs(want).max(), 1.0)
+
+
+# ---------------------------------------------------------------------------
+# state exchange and device-side reference profiles
+# ---------------------------------------------------------------------------
+def test_state_exchange_swaps_layouts_bit_exactly(dev):
+    """b.exchange(a) (suzerain/lowstorage.hpp:1511, suzerain/state.hpp:486-520,607-630) between the
+    interleaved and the contiguous layout, padded contiguous field stride, every stored pencil."""
+    import torch
+    from suzerain_b200 import lib as L
+    npen, n, pad = 37, 24, 5
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((npen, 5, n)) + 1j * rng.standard_normal((npen, 5, n))
+    b = rng.standard_normal((5, npen + pad, n)) + 1j * rng.standard_normal((5, npen + pad, n))
+    da, db = torch.from_numpy(a.copy()).to(dev), torch.from_numpy(b.copy()).to(dev)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check("szb_state_exchange", L.load().szb_state_exchange(npen, None, 5, n, _p(da), n, 5 * n, _p(db),
+                                                              (npen + pad) * n, n, s))
+    torch.cuda.synchronize()
+    ga, gb = da.cpu().numpy(), db.cpu().numpy()
+    assert np.array_equal(ga, np.transpose(b[:, :npen], (1, 0, 2)))
+    assert np.array_equal(gb[:, :npen], np.transpose(a, (1, 0, 2)))
+    assert np.array_equal(gb[:, npen:], b[:, npen:])                 # the padding is untouched
+
+
+def test_set_refs_device_equals_host_setter(dev):
+    """szb_imexop_set_refs_device gathers rows q::u .. q::e_deltarho of the reference's 42 x Ny column-major
+    `references` block (apps/perfect/references.hpp:82-125, references.cpp:50-108): same operator as the host
+    setter, bit for bit."""
+    import torch
+    case = pc.make_case("tiny_16x24x16", max_pencils=16)
+    want = pc.gpu_accumulate(case, dev)
+    op = pc.make_imexop(case)
+    op.set_refs(np.zeros_like(case.refs))                            # wipe, then restore through the device path
+    blk = np.full((case.n, 42), np.nan)
+    blk[:, 5:31] = case.refs.T
+    op.set_refs_device(torch.from_numpy(np.ascontiguousarray(blk)).to(dev))
+    km, kn = torch.from_numpy(case.km).to(dev), torch.from_numpy(case.kn).to(dev)
+    x = torch.from_numpy(case.x).to(dev)
+    y = torch.zeros_like(x)
+    op.accumulate_batch(case.phi, km, kn, x, 0.0, y)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy().reshape(len(case.km), -1), want)
+
+
+# ---------------------------------------------------------------------------
+# (kx,kz) sharding on real device shards
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("solver", ["zgbsv", "zcgbsvx"])
+def test_sharded_substep_matches_single_rank(dev, world, solver):
+    """One substep (accumulate -> exchange -> invert, with the per-step reference-profile reduction) on
+    `world` shards of the wave space -- shard.shard_wavegrid, each shard with its own operator context,
+    device state and stream, on its own GPU when the box has that many -- equals the single-rank result
+    bit for bit: wavenumbers are independent and nothing in L communicates."""
+    import torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import shard, synth
+    Nx, Ny, Nz, k, htdelta, _ = synth.CONFIGS["tiny_16x24x16"]
+    case = pc.make_case("tiny_16x24x16")
+    g = sz.wavegrid(Nx, Nz, synth.LX, synth.LZ)
+    km, kn, act = sz.wavenumbers(g)
+    npen = len(km)
+    state = synth.state(km, kn, Ny, synth.SEED)                          # (npen, 5, Ny)
+    pa, beta, pi = 2e-3 * synth.SMR91_ALPHA[1], 1e-4, -2e-3 * synth.SMR91_BETA[1]
+    spec = sz.SolverSpec(method=solver)
+    ngpu = torch.cuda.device_count()
+
+    def run(grid, st, device, stream, nparts):
+        with torch.cuda.device(device), torch.cuda.stream(stream):
+            op = pc.make_imexop(case)
+            # the profiles arrive as the sum of the ranks' contributions (perfect.cpp:1397)
+            blk = np.zeros((Ny, 42)); blk[:, 5:31] = case.refs.T
+            part = torch.from_numpy(blk / nparts).to(device)
+            total = torch.zeros_like(part)
+            for _ in range(nparts):
+                total += part
+            op.set_refs_device(total, stream=stream)
+            H = sz.OperatorHybridIsothermalDevice(op, grid, spec, device)
+            a = torch.from_numpy(st.copy()).to(device)
+            b = torch.full((5, H.npencil, Ny), 0.5 - 0.25j, dtype=torch.complex128, device=device)
+            H.accumulate_mass_plus_scaled_operator(pa, a, beta, b, stream=stream)
+            H.exchange(a, b, stream=stream)
+            H.invert_mass_plus_scaled_operator(pi, a, stream=stream)
+            stream.synchronize()
+            assert int(H.info.abs().max()) == 0
+            return a.cpu().numpy(), b.cpu().numpy()
+
+    nparts = 4                                                       # a power of two: the partial sums are exact
+    want_a, want_b = run(g, state, dev, torch.cuda.Stream(dev), nparts)
+    nx = g.dkex - g.dkbx
+    got_a, got_b = [], []
+    for r in range(world):
+        mine = shard.shard_wavegrid(g, r, world)
+        lo, hi = (mine.dkbz - g.dkbz) * nx, (mine.dkez - g.dkbz) * nx
+        d = torch.device("cuda", r % ngpu) if ngpu >= world else dev
+        ga, gb = run(mine, state[lo:hi], d, torch.cuda.Stream(d), nparts)
+        got_a.append(ga); got_b.append(gb)
+    assert np.array_equal(np.concatenate(got_a), want_a)
+    assert np.array_equal(np.concatenate(got_b, axis=1), want_b)
+    # and the single-rank result is the oracle's
+    P = pc.oracle_problem(case)
+    flat = state.reshape(npen, -1)
+    y = P.accumulate(pa, km[act], kn[act], flat[act], beta=beta, y=np.full_like(flat[act], 0.5 - 0.25j))
+    x = P.invert(solver, pi, km[act], kn[act], y)["x"]
+    assert pc.relmax(want_a.reshape(npen, -1)[act], x) <= TOL
+    assert np.all(want_a.reshape(npen, -1)[~act] == 0)
+
+
+# ---------------------------------------------------------------------------
+# larger samples of the big BASELINE grids; long run on the bench grid
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("config", ["channel_1536x384x1152", "bl_1024x256x512"])
+@pytest.mark.parametrize("solver", ["zgbsv", "zcgbsvx"])
+def test_big_grids_64_pencils_match_oracle(dev, config, solver):
+    """64+ wavenumber pairs of BASELINE configs 3 and 4 incl. the (0,0) mode and the largest |k|
+    (make_case always keeps both ends of the active list): solution to 1e-12, pivots identical."""
+    case = pc.make_case(config, max_pencils=64)
+    assert len(case.km) >= 64 and case.km[0] == 0 and case.kn[0] == 0
+    got = pc.gpu_invert(case, solver, dev)
+    want = pc.oracle_invert(case, solver, nthreads=8)
+    assert np.all(got["info"] == 0) and want["info"] == 0
+    if solver == "zgbsv":
+        assert np.array_equal(got["ipiv"], want["ipiv"]), "pivot choices differ"
+    assert pc.relmax(got["x"], want["x"]) <= TOL
+
+
+@pytest.mark.parametrize("solver", ["zgbsv", "zcgbsvx"])
+def test_hundred_time_steps_on_the_bench_grid(dev, solver):
+    """north_star: <= 1e-9 after 100 TIME STEPS (300 substeps) -- channel_192x96x192 (k = 8, Ny = 96), 200+
+    pencils, the SMR91 linear substeps (accumulate with beta = chi dt zeta_i, exchange, invert) with the
+    scheme's own coefficients, device against oracle substep by substep on the same evolving inputs."""
+    import torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import synth
+    case = pc.make_case("channel_192x96x192", max_pencils=200)
+    npen, n = len(case.km), case.n
+    assert npen >= 200
+    P = pc.oracle_problem(case)
+    op = pc.make_imexop(case)
+    km, kn = torch.from_numpy(case.km).to(dev), torch.from_numpy(case.kn).to(dev)
+    spec = sz.SolverSpec(method=solver)
+    a = torch.from_numpy(case.x.copy()).to(dev)
+    b = torch.zeros_like(a)
+    info = torch.zeros(npen, dtype=torch.int32, device=dev)
+    ha = case.x.reshape(npen, -1).copy()
+    hb = np.zeros_like(ha)
+    dt, chi = synth.delta_t(2.0), 1.0 / (288 * 288)
+    worst = 0.0
+    for it in range(300):
+        i = it % 3
+        pa, beta, pi = dt * synth.SMR91_ALPHA[i], chi * dt * synth.SMR91_ZETA[i], -dt * synth.SMR91_BETA[i]
+        op.accumulate_batch(pa, km, kn, a, beta, b)
+        a, b = b, a
+        op.invert_batch(spec, pi, km, kn, a, info=info)
+        hb = P.accumulate(pa, case.km, case.kn, ha, beta=beta, y=hb, nthreads=8)
+        ha, hb = hb, ha
+        ha = P.invert(solver, pi, case.km, case.kn, ha, nthreads=8)["x"]
+        if it % 30 == 29 or it == 299:
+            torch.cuda.synchronize()
+            assert int(info.abs().max()) == 0
+            worst = max(worst, pc.relmax(a.cpu().numpy().reshape(npen, -1), ha))
+    assert worst <= 1e-9, worst
