@@ -278,6 +278,16 @@ int szb_zcgbsvx_batch(char trans, int n, int kl, int ku, int aiter, int diter,
                       int *d_iters, double *d_res, int *d_info, int nbatch,
                       void *stream);
 
+/* bsmbsm_solver::solve for ONE system on HOST storage laid out as the reference's solver object keeps it
+ * (suzerain/bsmbsm_solver.hpp:70-330, .cpp:58-78): lu is (LD+KL) x N column-major; zgbsv works in place (the
+ * matrix sits in rows KL.. of lu, pb is overwritten by the solution, papt / px unused); zcgbsvx reads the
+ * unfactored papt (LD x N), writes the factors to lu and the solution to px, one refined solve per right hand
+ * side (bsmbsm_solver.cpp:396-401).  Returns zgbtrf's info.  include/suzerain_b200_solver.hpp wraps it in the
+ * reference's supply_B -> supplied_PAPT -> solve -> demand_X protocol. */
+int szb_bsmbsm_solver_solve(const szb_bsmbsm *A, const szb_zgbsv_spec *spec, char trans, int nrhs,
+                            szb_complex *lu, const szb_complex *papt, int *ipiv,
+                            szb_complex *pb, szb_complex *px, int *iters, double *res);
+
 /* ------------------------------------------------------------------------ *
  * Per-pencil HOST-pointer wrappers with the reference's signatures.
  * ------------------------------------------------------------------------ */

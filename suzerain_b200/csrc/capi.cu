@@ -460,6 +460,66 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
     return 0;
 }
 
+/* bsmbsm_solver::solve on HOST storage (suzerain/bsmbsm_solver.cpp:155-182 zgbsv, :377-414 zcgbsvx): the
+ * protocol object of include/suzerain_b200_solver.hpp keeps LU / PAPT / PB / PX / ipiv on the host exactly like
+ * the reference's; one call moves them to the device, runs the batched LAPACK kernels on this one system and
+ * brings the results back. */
+int szb_bsmbsm_solver_solve(const szb_bsmbsm *A, const szb_zgbsv_spec *spec, char trans, int nrhs,
+                            szb_complex *lu, const szb_complex *papt, int *ipiv,
+                            szb_complex *pb, szb_complex *px, int *iters, double *res)
+{
+    if (!A) return -1;
+    if (!spec) return -2;
+    if (trans != 'N' && trans != 'T') return -3;
+    if (nrhs < 0) return -4;
+    if (!lu) return -5;
+    if (!ipiv) return -7;
+    if (!pb) return -8;
+    if (nrhs == 0) return 0;
+    const int N = A->N, KL = A->KL, KU = A->KU, LD = A->LD, ldlu = LD + KL;
+    DevBuf<szb_complex> dlu, dpapt, db, dx; DevBuf<int> dipiv, dinfo, diters; DevBuf<double> dres;
+    SZB_CUDA_OK(dlu.alloc((size_t) ldlu * N)); SZB_CUDA_OK(dipiv.alloc(N)); SZB_CUDA_OK(dinfo.alloc(1));
+    SZB_CUDA_OK(db.alloc((size_t) N * nrhs));
+    int info = 0;
+    if (spec->method == SZB_SOLVER_ZGBSV) {
+        // in place: PAPT aliases LU + KL (bsmbsm_solver.cpp:64-67), PB is overwritten by the solution
+        SZB_CUDA_OK(cudaMemcpy(dlu.p, lu, sizeof(szb_complex) * ldlu * N, cudaMemcpyHostToDevice));
+        SZB_CUDA_OK(cudaMemcpy(db.p, pb, sizeof(szb_complex) * N * nrhs, cudaMemcpyHostToDevice));
+        int rc = szb_zgbtrf_batch(N, KL, KU, dlu.p, ldlu, (size_t) ldlu * N, dipiv.p, dinfo.p, 1, nullptr);
+        if (rc) return rc;
+        SZB_CUDA_OK(cudaMemcpy(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!info) {
+            rc = szb_zgbtrs_batch(trans, N, KL, KU, nrhs, dlu.p, ldlu, (size_t) ldlu * N, dipiv.p, db.p, N,
+                                  (size_t) N * nrhs, 1, nullptr);
+            if (rc) return rc;
+            SZB_CUDA_OK(cudaMemcpy(pb, db.p, sizeof(szb_complex) * N * nrhs, cudaMemcpyDeviceToHost));
+        }
+        SZB_CUDA_OK(cudaMemcpy(lu, dlu.p, sizeof(szb_complex) * ldlu * N, cudaMemcpyDeviceToHost));
+        SZB_CUDA_OK(cudaMemcpy(ipiv, dipiv.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+        return info;
+    }
+    if (spec->method != SZB_SOLVER_ZCGBSVX) return -2;      // zgbsvx has no pre-assembled entry point: say so
+    if (!papt) return -6;
+    if (!px) return -9;
+    SZB_CUDA_OK(dpapt.alloc((size_t) LD * N)); SZB_CUDA_OK(dx.alloc(N)); SZB_CUDA_OK(diters.alloc(1)); SZB_CUDA_OK(dres.alloc(1));
+    SZB_CUDA_OK(cudaMemcpy(dpapt.p, papt, sizeof(szb_complex) * LD * N, cudaMemcpyHostToDevice));
+    SZB_CUDA_OK(cudaMemcpy(db.p, pb, sizeof(szb_complex) * N * nrhs, cudaMemcpyHostToDevice));
+    for (int j = 0; j < nrhs && !info; ++j) {
+        // bsmbsm_solver_zcgbsvx::solve_hook refactors per right hand side too (gotcha 8)
+        int rc = szb_zcgbsvx_batch(trans, N, KL, KU, spec->aiter, spec->diter, spec->tolsc, dpapt.p, (size_t) LD * N,
+                                   dlu.p, (size_t) ldlu * N, dipiv.p, db.p + (size_t) j * N, dx.p, diters.p, dres.p,
+                                   dinfo.p, 1, nullptr);
+        if (rc) return rc;
+        SZB_CUDA_OK(cudaMemcpy(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost));
+        SZB_CUDA_OK(cudaMemcpy(px + (size_t) j * N, dx.p, sizeof(szb_complex) * N, cudaMemcpyDeviceToHost));
+        if (iters) SZB_CUDA_OK(cudaMemcpy(iters + j, diters.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (res) SZB_CUDA_OK(cudaMemcpy(res + j, dres.p, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    SZB_CUDA_OK(cudaMemcpy(lu, dlu.p, sizeof(szb_complex) * ldlu * N, cudaMemcpyDeviceToHost));
+    SZB_CUDA_OK(cudaMemcpy(ipiv, dipiv.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    return info;
+}
+
 /* The km = kn = 0 special cases (suzerain/rholut_imexop.h:209-238, 330-368, 447-469: "equivalent
  * to calling ... using km == 0 and kn == 0"), used by linearize::rhome_y. */
 int szb_rholut_imexop_accumulate00(const double phi[2],

@@ -112,6 +112,8 @@ PROTOTYPES = {
                                           C.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
     "szb_imexop_workspace_bytes": (C.c_size_t, [c_void_p]),
+    "szb_bsmbsm_solver_solve": (C.c_int, [C.POINTER(Bsmbsm), C.POINTER(ZgbsvSpec), C.c_char, C.c_int, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "szb_state_exchange": (C.c_int, [C.c_int, c_void_p, C.c_int, C.c_int, c_void_p, C.c_size_t, C.c_size_t,
                                      c_void_p, C.c_size_t, C.c_size_t, c_void_p]),
     "szb_zero_pencils": (C.c_int, [C.c_int, c_void_p, C.c_int, C.c_int, c_void_p, C.c_size_t,

@@ -315,3 +315,162 @@ def test_hundred_time_steps_on_the_bench_grid(dev, solver):
             assert int(info.abs().max()) == 0
             worst = max(worst, pc.relmax(a.cpu().numpy().reshape(npen, -1), ha))
     assert worst <= 1e-9, worst
+
+
+# ---------------------------------------------------------------------------
+# the drop-in library: the reference's own per-pencil symbols (include/suzerain_b200_dropin.h)
+# ---------------------------------------------------------------------------
+class _Cplx(C.Structure):
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+
+class _Workspace(C.Structure):
+    """suzerain_bsplineop_workspace (suzerain/bsplineop.h:125-180)."""
+    _fields_ = [("method", C.c_int), ("k", C.c_int), ("n", C.c_int), ("nderiv", C.c_int),
+                ("kl", C.POINTER(C.c_int)), ("ku", C.POINTER(C.c_int)),
+                ("max_kl", C.c_int), ("max_ku", C.c_int), ("ld", C.c_int),
+                ("D_T", C.POINTER(C.POINTER(C.c_double)))]
+
+
+def _reference_workspace(bop):
+    """A reference-layout workspace over a copy of the operator storage: D_T[d] points max_ku - ku[d]
+    doubles into derivative d's block (bsplineop.c:163-187)."""
+    from suzerain_b200 import lib as L
+    st = np.ascontiguousarray(bop.storage)                      # (nderiv+1, n, ld)
+    kl = (C.c_int * len(bop.kl))(*[int(v) for v in bop.kl])
+    ku = (C.c_int * len(bop.ku))(*[int(v) for v in bop.ku])
+    base = st.ctypes.data
+    ptrs = (C.POINTER(C.c_double) * (bop.nderiv + 1))()
+    for d in range(bop.nderiv + 1):
+        addr = base + 8 * (d * bop.n * bop.ld + int(bop.max_ku - bop.ku[d]))
+        ptrs[d] = C.cast(C.c_void_p(addr), C.POINTER(C.c_double))
+    w = _Workspace(0, bop.k, bop.n, bop.nderiv, kl, ku, bop.max_kl, bop.max_ku, bop.ld, ptrs)
+    return w, (st, kl, ku, ptrs)                                  # keep-alives
+
+
+def _dropin():
+    path = os.path.join(pc.ROOT, "suzerain_b200", "libsuzerain_b200_dropin.so")
+    return C.CDLL(path)
+
+
+def _ref_structs(case, refs):
+    from suzerain_b200 import lib as L
+    r, ld = L.Ref(), L.RefLd()
+    keep = []
+    for q, name in enumerate(L.REF_NAMES):
+        col = np.ascontiguousarray(refs[q])
+        keep.append(col)
+        setattr(r, name, col.ctypes.data_as(L.c_double_p))
+        setattr(ld, name, 1)
+    s = L.Scenario(*[case.scenario[k] for k in ("Re", "Pr", "Ma", "alpha", "gamma")])
+    return s, r, ld, keep
+
+
+@pytest.mark.parametrize("nrbc", [False, True])
+def test_dropin_per_pencil_functions_match_the_reference(dev, nrbc):
+    """tests/test_rholut_imexop.cpp:86-302 replayed through the reference's own symbols as the drop-in library
+    exports them (complex by value, the five ordering integers, buf): k = 6, n = 10, every one of the 26
+    reference profiles switched on alone (and all together), packc and packf against the reference's assembly,
+    accumulate against the reference's apply, packf == packc shifted by KL rows, NaN-poisoned storage keeps
+    its NaNs outside the band."""
+    import suzerain_b200 as sz
+    from suzerain_b200 import lib as L
+    k, n = 6, 10
+    bp = np.linspace(0.0, 2.0, n - k + 2) ** 1.3
+    bop = sz.BsplineOp.from_breakpoints(k, bp)
+    base = pc.make_case("tiny_16x24x16", max_pencils=4, Ny=n, k=k)
+    lib = _dropin()
+    w, keep_w = _reference_workspace(bop)
+    A = L.load().szb_bsmbsm_construct(5, n, bop.max_kl, bop.max_ku)
+    N, KL, LD = A.N, A.KL, A.LD
+    rng = np.random.default_rng(42)
+    abc = [np.asfortranarray(0.3 * rng.standard_normal((5, 5))).reshape(-1, order="F") for _ in range(3)] if nrbc else None
+    km, kn, phi = 0.7, -1.3, complex(-0.02, 0.005)
+    x = rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))
+    y0 = rng.standard_normal((5, n)) + 1j * rng.standard_normal((5, n))
+    beta = complex(0.6, -0.3)
+    pd = lambda arr: None if arr is None else arr.ctypes.data_as(L.c_double_p)
+    for which in list(range(26)) + [None]:
+        refs = np.zeros((26, n))
+        if which is None:
+            refs = rng.standard_normal((26, n))
+        else:
+            refs[which] = rng.standard_normal(n)
+        case = pc.Case("dropin", bop, refs, base.scenario, base.walls, tuple(abc) if nrbc else None,
+                       np.array([km]), np.array([kn]), x[None].copy(), phi, nrbc)
+        P = pc.oracle_problem(case)
+        s, r, ld, keep = _ref_structs(case, refs)
+        a, b, c = (abc if nrbc else (None, None, None))
+        # ---- packc / packf ----
+        want_c = P.assemble(phi, km, kn, packf=False, with_bc=False)          # (N, LD)
+        got_c = np.full((N, LD), np.nan + 1j * np.nan)
+        got_f = np.full((N, LD + KL), np.nan + 1j * np.nan)
+        for fn, buf_out in ((lib.suzerain_rholut_imexop_packc, got_c), (lib.suzerain_rholut_imexop_packf, got_f)):
+            fn.restype = None
+            fn(_Cplx(phi.real, phi.imag), C.c_double(km), C.c_double(kn), C.byref(s), C.byref(r), C.byref(ld),
+               C.byref(w), 0, 1, 2, 3, 4, None, C.byref(A), buf_out.ctypes.data_as(C.c_void_p), pd(a), pd(b), pd(c))
+        inband = ~np.isnan(want_c.real)
+        assert np.array_equal(np.isnan(got_c.real), ~inband)                    # NaNs survive outside the band only
+        scale = max(np.abs(want_c[inband]).max(), 1e-300)
+        assert np.abs(got_c[inband] - want_c[inband]).max() <= 1e-13 * scale
+        assert np.all(np.isnan(got_f[:, :KL].real))                             # the factorisation rows stay untouched
+        assert np.array_equal(got_f[:, KL:][inband], got_c[inband])             # packf == packc (test :215-230)
+        # ---- accumulate ----
+        want_y = P.accumulate(phi, np.array([km]), np.array([kn]), x.reshape(1, -1), beta=beta, y=y0.reshape(1, -1).copy())
+        yy = [np.ascontiguousarray(y0[f]) for f in range(5)]
+        xx = [np.ascontiguousarray(x[f]) for f in range(5)]
+        fn = lib.suzerain_rholut_imexop_accumulate
+        fn.restype = None
+        pv = lambda arr: arr.ctypes.data_as(C.c_void_p)
+        fn(_Cplx(phi.real, phi.imag), C.c_double(km), C.c_double(kn), C.byref(s), C.byref(r), C.byref(ld), C.byref(w),
+           pv(xx[0]), pv(xx[1]), pv(xx[2]), pv(xx[3]), pv(xx[4]), _Cplx(beta.real, beta.imag),
+           pv(yy[0]), pv(yy[1]), pv(yy[2]), pv(yy[3]), pv(yy[4]), pd(a), pd(b), pd(c))
+        got_y = np.concatenate(yy)
+        assert pc.relmax(got_y, want_y.reshape(-1)) <= TOL
+
+
+# ---------------------------------------------------------------------------
+# the C++ bsmbsm_solver drop-in (include/suzerain_b200_solver.hpp)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["zgbsv", "zcgbsvx"])
+def test_cxx_bsmbsm_solver_protocol(dev, method, tmp_path):
+    """supply_B -> PAPT -> supplied_PAPT -> solve('T') -> demand_X through the header-only C++ class
+    (suzerain/bsmbsm_solver.hpp:70-330 protocol), compiled here with g++, against the reference's zgbtrf +
+    zgbtrs('T') with the permutations written out; two right hand sides."""
+    import subprocess
+    from suzerain_b200 import lib as L
+    from oracle import ref as oref
+    case = pc.make_case("tiny_16x24x16", max_pencils=3)
+    papt = pc.oracle_assemble(case, 1, packf=False, with_bc=True)          # (N, LD)
+    N, LD = papt.shape
+    KL = KU = (LD - 1) // 2
+    n = case.n
+    kl = ku = (KL + 1) // 5 - 1
+    nrhs = 2
+    rng = np.random.default_rng(9)
+    b = rng.standard_normal((nrhs, N)) + 1j * rng.standard_normal((nrhs, N))
+    src = os.path.join(pc.ROOT, "tests", "cxx", "solver_protocol.cpp")
+    exe = str(tmp_path / "solver_protocol")
+    libdir = os.path.join(pc.ROOT, "suzerain_b200")
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(pc.ROOT, "include"), src, "-o", exe,
+                    "-L" + libdir, "-lsuzerain_b200", "-Wl,-rpath," + libdir], check=True)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        np.array([5, n, kl, ku, nrhs], dtype=np.int32).tofile(f)
+        b.astype(np.complex128).tofile(f)
+        np.where(np.isnan(papt), 0, papt).astype(np.complex128).tofile(f)
+    subprocess.run([exe, fin, fout, method], check=True)
+    raw = open(fout, "rb").read()
+    info = np.frombuffer(raw[:4], dtype=np.int32)[0]
+    ipiv = np.frombuffer(raw[4:4 + 4 * N], dtype=np.int32)
+    x = np.frombuffer(raw[4 + 4 * N:], dtype=np.complex128).reshape(nrhs, N)
+    assert info == 0
+    lib = L.load()
+    q = np.array([lib.szb_bsmbsm_q(5, n, i) for i in range(N)])
+    ab = np.zeros((N, 2 * KL + KU + 1), dtype=np.complex128)
+    ab[:, KL:] = np.where(np.isnan(papt), 0, papt)
+    _, piv, X, rinfo = oref.zgbsv_T(N, KL, KU, ab, b[:, q])                    # P b
+    want = np.empty_like(X)
+    want[:, q] = X                                                             # P^T x
+    assert rinfo == 0 and np.array_equal(ipiv, piv)
+    assert pc.relmax(x, want) <= TOL
