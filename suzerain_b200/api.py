@@ -464,6 +464,22 @@ class OperatorHybridIsothermalDevice:
                                         y_strides=None if interleaved_output else (n * self.npencil, n),
                                         stream=stream)
 
+    def raise_on_singular(self):
+        """The device-resident invert records zgbtrf's info per active pencil in ``self.info`` without
+        stopping; call this (it synchronises) where a singular operator must be fatal, as it is in the
+        reference (bsmbsm_solver.cpp:123-141 -> SUZERAIN_ERROR).  lowstorage.step does so once per step."""
+        info = self.info[:self.nactive]
+        if self.nactive and bool((info != 0).any()):
+            import torch
+            bad = int(torch.nonzero(info)[0])
+            rc = int(info[bad])
+            n = self.op.n
+            row = rc - 1
+            q = (row % 5) * n + row // 5
+            raise _L.SzbError(
+                f"invert: pencil {int(self.h_active[bad])}: singularity in PAP^T row {row} corresponding to "
+                f"A row {q} for state scalar {q // n}", rc)
+
     def exchange(self, a, b, stream=None):
         """a <-> b between the interleaved state a (npencil, 5, Ny) and the contiguous state b (5, npencil, Ny):
         `b.exchange(a)` of lowstorage::step (suzerain/lowstorage.hpp:1511), every stored pencil."""

@@ -685,7 +685,7 @@ int szb_imexop_invert_batch(const szb_imexop *op, const szb_zgbsv_spec *spec,
             if (op->d_zero) SZB_CUDA_OK(cudaFree(op->d_zero));
             op->d_zero = nullptr; op->zero_count = 0;
             SZB_CUDA_OK(cudaMalloc(&op->d_zero, sizeof(double) * (size_t) npencil));
-            SZB_CUDA_OK(cudaMemset(op->d_zero, 0, sizeof(double) * (size_t) npencil));
+            SZB_CUDA_OK(cudaMemsetAsync(op->d_zero, 0, sizeof(double) * (size_t) npencil, (cudaStream_t) stream));
             op->zero_count = (size_t) npencil;
         }
         d_km = d_kn = op->d_zero;

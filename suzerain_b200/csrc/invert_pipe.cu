@@ -1109,7 +1109,9 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                             int *d_iters, cudaStream_t stream)
 {
+    // applicability first: nothing may have been launched when the caller is told to fall back
     if (op->A.KL != op->A.KU || dmax < 0) return 1;
+    if (!mode && aiter < 1) return 1;       // lastres starts at 3: exact for aiter >= 1 (dsgbsvx.def:271-284)
     const int N = op->A.N, n = op->n;
     // workspace: b, r | res, lastres, kma, kna | diter, cont, pos, info2, count
     const size_t nb = (size_t) npencil * N * sizeof(cplx);
@@ -1153,7 +1155,6 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
     A.res = res; A.lastres = lastres; A.diter = diter; A.cont = cont;
     // the reference starts from lastres = 3 (|b| + 1): never a stagnation at it = 0 unless aiter = 0;
     // with aiter = 0 the test lastres < 2 res needs |b|: keep it simple and exact for aiter >= 1
-    if (aiter < 1) return 1;
     // zcgbsvx: the residual is the operator applied to the solution -- accumulate_kernel (0.25 ms for 18 336
     // pencils) plus a small fix-up kernel instead of re-assembling every row block (7.4 ms).  SZB_REFINE_ACC=0
     // keeps the assembling kernel, which zgbsvx (mode 1: it needs |A^T| |x| too) always uses.

@@ -122,6 +122,10 @@ class InterleavedOperator:
     def invert_mass_plus_scaled_operator(self, phi, state):
         return self.H.invert_mass_plus_scaled_operator(phi, state, stream=self.stream)
 
+    def raise_on_singular(self):
+        """Fatal singular pencils as in the reference (bsmbsm_solver.cpp:123-141); synchronises."""
+        self.H.raise_on_singular()
+
 
 def delta_t_reducer(candidates):
     """lowstorage::delta_t_reducer: the smallest stable candidate (NaN propagates)."""
@@ -160,4 +164,8 @@ def step(m, reducer, L, chi, N, time, a, b, max_delta_t=0.0):
         N.apply_operator(time + delta_t * m.eta(i), b, m, i)
         a.add_scaled(chi * delta_t * m.gamma(i), b)
         L.invert_mass_plus_scaled_operator(-delta_t * m.beta(i), a.data)
+    # a device-resident operator records zgbtrf's info per pencil instead of stopping mid-step: make a singular
+    # operator fatal here as it is in the reference (bsmbsm_solver.cpp:123-141); one synchronisation per step
+    if hasattr(L, "raise_on_singular"):
+        L.raise_on_singular()
     return delta_t

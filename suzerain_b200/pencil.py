@@ -210,27 +210,33 @@ class PencilGrid:
             self._check(b)
         dev = bufs[0].device
         self._resolve_exchange(dev)
-        L, h, s = load(), c_void_p(self._h), self._stream(stream)
+        import torch
+        ts = stream or torch.cuda.current_stream(dev)
+        L, h, s = load(), c_void_p(self._h), c_void_p(ts.cuda_stream)
         rc = 0
         if self.nranks == 1:
             for b in bufs:
                 rc = rc or L.szb_pencil_grid_transform_wave_to_physical(h, c_void_p(b.data_ptr()), s)
-        elif self.exchange == "p2p":
-            P = self._p2p_setup(dev, len(bufs))
-            P["hf"].barrier(channel=0)                      # every peer's FFT buffers are free again
-            for f, b in enumerate(bufs):
-                rc = rc or L.szb_pencil_grid_w2p_pack_peers(h, c_void_p(b.data_ptr()), P["pf"][f], s)
-            P["hf"].barrier(channel=1)                      # every block has landed
-            for f, b in enumerate(bufs):
-                rc = rc or L.szb_pencil_grid_w2p_fft(h, c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]),
-                                                     c_void_p(b.data_ptr()), s)
         else:
-            send, recv, ns, nr = self._exchange_buffers(0, dev)
-            for b in bufs:
-                rc = rc or L.szb_pencil_grid_w2p_pack(h, c_void_p(b.data_ptr()), c_void_p(send.data_ptr()), s)
-                if rc == 0:
-                    self._all_to_all(recv, send, nr, ns)
-                    rc = L.szb_pencil_grid_w2p_finish(h, c_void_p(recv.data_ptr()), c_void_p(b.data_ptr()), s)
+            # the symmetric-memory barriers, NCCL and torch copies are issued on torch's CURRENT stream: make the
+            # caller's stream current so that kernels, barriers and the exchange are ordered on one stream.  Every
+            # barrier / collective is executed even after a failed launch: the peers are waiting in theirs.
+            with torch.cuda.stream(ts):
+                if self.exchange == "p2p":
+                    P = self._p2p_setup(dev, len(bufs))
+                    P["hf"].barrier(channel=0)                      # every peer's FFT buffers are free again
+                    for f, b in enumerate(bufs):
+                        rc = rc or L.szb_pencil_grid_w2p_pack_peers(h, c_void_p(b.data_ptr()), P["pf"][f], s)
+                    P["hf"].barrier(channel=1)                      # every block has landed
+                    for f, b in enumerate(bufs):
+                        rc = rc or L.szb_pencil_grid_w2p_fft(h, c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]),
+                                                             c_void_p(b.data_ptr()), s)
+                else:
+                    send, recv, ns, nr = self._exchange_buffers(0, dev)
+                    for b in bufs:
+                        rc = rc or L.szb_pencil_grid_w2p_pack(h, c_void_p(b.data_ptr()), c_void_p(send.data_ptr()), s)
+                        self._all_to_all(recv, send, nr, ns)
+                        rc = rc or L.szb_pencil_grid_w2p_finish(h, c_void_p(recv.data_ptr()), c_void_p(b.data_ptr()), s)
         if rc:
             raise RuntimeError(f"transform_wave_to_physical failed: {rc}")
 
@@ -239,28 +245,31 @@ class PencilGrid:
             self._check(b)
         dev = bufs[0].device
         self._resolve_exchange(dev)
-        L, h, s = load(), c_void_p(self._h), self._stream(stream)
+        import torch
+        ts = stream or torch.cuda.current_stream(dev)
+        L, h, s = load(), c_void_p(self._h), c_void_p(ts.cuda_stream)
         rc = 0
         if self.nranks == 1:
             for b in bufs:
                 rc = rc or L.szb_pencil_grid_transform_physical_to_wave(h, c_void_p(b.data_ptr()), s)
-        elif self.exchange == "p2p":
-            P = self._p2p_setup(dev, len(bufs))
-            for f, b in enumerate(bufs):
-                rc = rc or L.szb_pencil_grid_p2w_fft(h, c_void_p(b.data_ptr()), c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]), s)
-            P["hw"].barrier(channel=0)                      # every peer's wave buffers are free again
-            for f, b in enumerate(bufs):
-                rc = rc or L.szb_pencil_grid_p2w_scatter_peers(h, c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]), P["pw"][f], s)
-            P["hw"].barrier(channel=1)
-            nx, ny, nz = self.local_wave_extent
-            for f, b in enumerate(bufs):
-                b[:2 * nx * ny * nz].copy_(P["wave"][f * P["sw"]:f * P["sw"] + 2 * nx * ny * nz])
         else:
-            send, recv, ns, nr = self._exchange_buffers(1, dev)
-            for b in bufs:
-                rc = rc or L.szb_pencil_grid_p2w_start(h, c_void_p(b.data_ptr()), c_void_p(send.data_ptr()), s)
-                if rc == 0:
-                    self._all_to_all(recv, send, nr, ns)
-                    rc = L.szb_pencil_grid_p2w_unpack(h, c_void_p(recv.data_ptr()), c_void_p(b.data_ptr()), s)
+            with torch.cuda.stream(ts):                             # see transform_wave_to_physical_many
+                if self.exchange == "p2p":
+                    P = self._p2p_setup(dev, len(bufs))
+                    for f, b in enumerate(bufs):
+                        rc = rc or L.szb_pencil_grid_p2w_fft(h, c_void_p(b.data_ptr()), c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]), s)
+                    P["hw"].barrier(channel=0)                      # every peer's wave buffers are free again
+                    for f, b in enumerate(bufs):
+                        rc = rc or L.szb_pencil_grid_p2w_scatter_peers(h, c_void_p(P["fft"].data_ptr() + 8 * f * P["sf"]), P["pw"][f], s)
+                    P["hw"].barrier(channel=1)
+                    nx, ny, nz = self.local_wave_extent
+                    for f, b in enumerate(bufs):
+                        b[:2 * nx * ny * nz].copy_(P["wave"][f * P["sw"]:f * P["sw"] + 2 * nx * ny * nz])
+                else:
+                    send, recv, ns, nr = self._exchange_buffers(1, dev)
+                    for b in bufs:
+                        rc = rc or L.szb_pencil_grid_p2w_start(h, c_void_p(b.data_ptr()), c_void_p(send.data_ptr()), s)
+                        self._all_to_all(recv, send, nr, ns)
+                        rc = rc or L.szb_pencil_grid_p2w_unpack(h, c_void_p(recv.data_ptr()), c_void_p(b.data_ptr()), s)
         if rc:
             raise RuntimeError(f"transform_physical_to_wave failed: {rc}")

@@ -113,3 +113,43 @@ def test_restart_loader_on_the_bench_grid_file():
     prof = r.mean_profiles(bop)
     assert prof["bar_rho"].shape == (1, 96) and prof["bar_u"].shape == (3, 96)
     assert abs(prof["bar_u"][0, 0]) <= 1e-14 and 0.5 < prof["bar_rho"].min()
+
+
+def test_restart_state_translates_wavenumbers_into_the_dealiased_grid():
+    """A three-dimensional restart field is (Nz, Nx/2+1, Ny), not dealiased and in order in kz
+    (support/field.cpp:132-135); Restart.state scatters it into the dealiased (dNz, dNx/2+1) wave space with
+    the reference's wavenumber translation (field.cpp:184-207, inorder.c:75-151).  The shipped fixtures are
+    all Nx = Nz = 1, so this case is synthetic."""
+    import suzerain_b200 as sz
+    from suzerain_b200 import restart
+    Nx, Ny, Nz = 8, 5, 6
+    rng = np.random.default_rng(0)
+    fields = {n: rng.standard_normal((Nz, Nx // 2 + 1, Ny)) + 1j * rng.standard_normal((Nz, Nx // 2 + 1, Ny))
+              for n in restart.FIELDS}
+    R = restart.Restart(path="synthetic", Nx=Nx, Ny=Ny, Nz=Nz, k=4, htdelta=0.0, Lx=4 * np.pi, Ly=2.0, Lz=2 * np.pi,
+                        DAFx=1.5, DAFz=1.5, t=0.0, scenario={}, breakpoints_y=None, collocation_points_y=None,
+                        operators={}, fields=fields, samples={})
+    dNz, nx = R.wave_extents()
+    assert (dNz, nx) == (9, 7)
+    st = R.state().reshape(dNz, nx, 5, Ny)
+    g = sz.wavegrid(Nx, Nz, R.Lx, R.Lz)
+    km, kn, act = sz.wavenumbers(g)
+    assert st.shape[0] * st.shape[1] == len(km)
+    wz = lambda i, N: i if i < N // 2 + 1 else i - N
+    seen = np.zeros((dNz, nx), dtype=bool)
+    for iz in range(Nz):
+        for ix in range(Nx // 2 + 1):
+            w = wz(iz, Nz)
+            jz = w if w >= 0 else dNz + w
+            for f, n in enumerate(restart.FIELDS):
+                assert np.array_equal(st[jz, ix, f], fields[n][iz, ix]), (iz, ix, n)
+            seen[jz, ix] = True
+    assert np.all(st[~seen] == 0)                                  # the dealiasing band is empty
+    # every active pencil of the operator's walk carries a file mode; (kx, kz) agree with the wavenumber tables
+    flat_seen = seen.reshape(-1)
+    assert np.all(flat_seen[act])
+    two_pi_Lz = 2 * np.pi / R.Lz
+    assert np.isclose(kn.reshape(dNz, nx)[dNz - 1, 0], -two_pi_Lz)     # kz = -1 sits in the last row
+    # a finer file than the target keeps only the modes the target can hold
+    s, d = restart.wavenumber_translate(8, 4)
+    assert s.tolist() == [0, 1, 2, 7] and d.tolist() == [0, 1, 2, 3]
