@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=${1:-r2n}
+timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q --timeout 300 -x > gpurun_out/${TAG}_tests.log 2>&1
+echo "tests rc=$?"; tail -4 gpurun_out/${TAG}_tests.log
+for i in 1 2; do python tools/prof_invert.py channel_192x96x192 18336 2>&1 | grep "invert" | tail -1; done
+SZB_LIB=suzerain_b200/variants/libprof.so timeout -s KILL 200 python tools/prof_sync.py channel_192x96x192 18336 2>&1 | tail -4 | tee gpurun_out/${TAG}_prof.log
+SZB_LIB=suzerain_b200/variants/libprof.so timeout -s KILL 600 python tools/diag_balance.py channel_1536x384x1152 8 2>&1 | tail -8 | tee gpurun_out/${TAG}_balance.log
