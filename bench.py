@@ -68,6 +68,8 @@ def parse_args():
     ap.add_argument("--config", default=None, help="named grid; default: the BASELINE.json grid for --gpus")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: ONE named grid sharded over the ranks; weak: a whole copy per rank")
+    ap.add_argument("--balance", default="cost", choices=["cost", "active"],
+                    help="sharding weights: measured row cost (default) or active pencils per row")
     ap.add_argument("--solver", default=DEFAULT_SOLVER, choices=["zgbsv", "zcgbsvx"])
     ap.add_argument("--no-second-solver", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -89,7 +91,7 @@ class Workload:
     """Synthetic turbulent-channel / boundary-layer operator and state of one named grid,
     or of this rank's shard of it."""
 
-    def __init__(self, name, rank=0, world=1, sharded=True):
+    def __init__(self, name, rank=0, world=1, sharded=True, row_weights=None):
         import suzerain_b200 as sz
         from suzerain_b200 import synth, shard
         self.name = name
@@ -104,7 +106,7 @@ class Workload:
         self.nrbc = synth.nrbc_matrices() if one_sided else None
         self.full_grid = sz.wavegrid(Nx, Nz, synth.LX, synth.LZ)
         self.sharded = sharded and world > 1
-        self.grid = shard.shard_wavegrid(self.full_grid, rank, world) if self.sharded else self.full_grid
+        self.grid = shard.shard_wavegrid(self.full_grid, rank, world, row_weights) if self.sharded else self.full_grid
         km, kn, act = sz.wavenumbers(self.grid)
         self.km, self.kn, self.act = km, kn, act
         self.npencil, self.nactive = len(km), int(act.sum())
@@ -360,6 +362,46 @@ def bind_to_gpu_numa_node(local):
         return f"unbound ({type(e).__name__})"
 
 
+def row_cost_weights(wl_full, op, dev, nbuckets=24, per_bucket=1184):
+    """Measured cost of every kz row of the whole grid for the sharding (suzerain_b200/shard.py): the fused
+    invert is timed on a sample of the active pencils of `nbuckets` groups of rows; a row weighs its active
+    pencils times its group's time per pencil.  Run on rank 0 and broadcast, so that all ranks cut alike."""
+    import torch
+    import suzerain_b200 as sz
+    from suzerain_b200 import shard
+    g = wl_full.full_grid
+    nx = g.dkex - g.dkbx
+    nrows = g.dkez - g.dkbz
+    act_rows = shard.active_rows(g).astype(np.float64)
+    km = wl_full.km.reshape(nrows, nx); kn = wl_full.kn.reshape(nrows, nx); act = wl_full.act.reshape(nrows, nx)
+    spec = sz.SolverSpec(method="zgbsv")
+    pi = wl_full.phis(0)[2]
+    cost = np.ones(nrows)
+    edges = np.linspace(0, nrows, nbuckets + 1).astype(int)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for b in range(nbuckets):
+        r0, r1 = edges[b], edges[b + 1]
+        m = act[r0:r1]
+        if not m.any():
+            continue
+        kmb, knb = km[r0:r1][m], kn[r0:r1][m]
+        sel = np.linspace(0, len(kmb) - 1, min(per_bucket, len(kmb))).astype(int)
+        kmt, knt = torch.from_numpy(kmb[sel]).to(dev), torch.from_numpy(knb[sel]).to(dev)
+        x = torch.from_numpy(wl_full.synth.state(kmb[sel], knb[sel], wl_full.Ny, 7)).to(dev)
+        info = torch.zeros(len(sel), dtype=torch.int32, device=dev)
+        best = None
+        for rep in range(3):
+            xx = x.clone()
+            e0, e1 = ev(), ev()
+            e0.record(); op.invert_batch(spec, pi, kmt, knt, xx, info=info); e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        cost[r0:r1] = best / len(sel)
+    cost /= cost[cost > 0].min() if (cost > 0).any() else 1.0
+    return act_rows * cost
+
+
 def mem_available_bytes():
     try:
         for ln in open("/proc/meminfo"):
@@ -394,7 +436,20 @@ def run_b200(args):
 
     lib = L.load()
     sharded = args.scaling == "strong"
-    wl = Workload(args.config, rank, world, sharded)
+    weights = None
+    balance = "active pencils"
+    if sharded and world > 1 and args.balance == "cost":
+        # static load balancing on measured row costs: rank 0 probes, everybody cuts alike
+        wl_full = Workload(args.config)
+        op0 = wl_full.make_imexop()
+        w = torch.zeros(wl_full.full_grid.dkez - wl_full.full_grid.dkbz, dtype=torch.float64, device=dev)
+        if rank == 0:
+            w.copy_(torch.from_numpy(row_cost_weights(wl_full, op0, dev)))
+        dist.broadcast(w, src=0)
+        weights = w.cpu().numpy()
+        balance = "measured row cost (fused invert timed on a sample of every group of kz rows by rank 0, broadcast)"
+        del op0, wl_full
+    wl = Workload(args.config, rank, world, sharded, weights)
     op = wl.make_imexop()
     n, npen = wl.Ny, wl.npencil
     stream = torch.cuda.current_stream()
@@ -573,6 +628,8 @@ def run_b200(args):
     except Exception:
         fp64_peak = 34.17
     line = base_line(args, wl, world)
+    if world > 1 and sharded:
+        line["config"]["balance"] = balance
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
     kernels = {"accumulate": {"ms": acc_ms, "GB/s": gbs(acc_bytes, acc_ms), "frac": gbs(acc_bytes, acc_ms) / peak,
                               "algorithmic_bytes": acc_bytes, "traffic": tr("accumulate")},

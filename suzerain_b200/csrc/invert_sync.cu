@@ -672,7 +672,10 @@ template <class W, bool IG>
 int launch_sync_ig(const szb_imexop *op, PipeArgs &A, int npencil, cudaStream_t stream)
 {
     const int N = op->A.N;
-    const size_t smem = SyncLayout<W>::bytes(N, IG);
+    size_t smem = SyncLayout<W>::bytes(N, IG);
+    // experiment switch: extra dynamic shared memory lowers the number of CTAs per SM (SZB_SYNC_PAD bytes)
+    static const size_t pad = [] { const char *e = std::getenv("SZB_SYNC_PAD"); return e ? (size_t) std::atol(e) : (size_t) 0; }();
+    smem += pad;
     if (smem > 227 * 1024) return 1;                 // caller falls back to another kernel
     static bool configured = false;
     if (!configured) {

@@ -48,9 +48,13 @@ def shard_bounds(weights, world):
     return bounds
 
 
-def shard_wavegrid(grid, rank, world):
-    """The sub-grid (same global extents, narrower local kz range) owned by `rank`."""
-    b = shard_bounds(active_rows(grid), world)
+def shard_wavegrid(grid, rank, world, weights=None):
+    """The sub-grid (same global extents, narrower local kz range) owned by `rank`.  `weights`: cost of every
+    local kz row (default: its number of active pencils).  The banded solve of a pencil costs more where its
+    pivot sequence leaves the diagonal -- up to 29 % of the panels at the highest wavenumbers of the
+    1536x384x1152 grid against 3 % elsewhere -- so a stepper may pass measured row costs instead
+    (bench.py: row_cost_weights); every rank must use the same weights."""
+    b = shard_bounds(active_rows(grid) if weights is None else weights, world)
     return _L.WaveGrid(grid.Nx, grid.dNx, grid.dkbx, grid.dkex, grid.Nz, grid.dNz,
                        grid.dkbz + b[rank], grid.dkbz + b[rank + 1], grid.Lx, grid.Lz)
 

@@ -72,3 +72,31 @@ def test_two_rank_sharding_matches_single_rank():
     assert same_shape and sum(sizes) == 13 * 24         # (dNx/2+1) * dNz stored pencils (Nx=Nz=16, dN=24)
     assert err <= 1e-14                                  # same arithmetic, only partitioned
     assert zz == 0
+
+
+def test_cost_weighted_shards_cover_the_grid_and_balance_the_weights():
+    """shard_wavegrid with measured row costs (bench.py: row_cost_weights): contiguous blocks that cover every kz
+    row exactly once, with block weights within one row of the ideal share."""
+    sys.path.insert(0, ROOT)
+    import suzerain_b200 as sz
+    from suzerain_b200 import shard, synth
+    g = sz.wavegrid(64, 48, synth.LX, synth.LZ)
+    act = shard.active_rows(g).astype(float)
+    n = len(act)
+    # rows near the largest |kz| cost 1.6 times the others, as on the big channel grid
+    wz = np.array([i if i < g.dNz // 2 + 1 else i - g.dNz for i in range(n)])
+    w = act * np.where(np.abs(wz) > 0.6 * (g.Nz // 2), 1.6, 1.0)
+    for world in (2, 3, 4, 8):
+        rows, sums = [], []
+        for r in range(world):
+            m = shard.shard_wavegrid(g, r, world, w)
+            rows += list(range(m.dkbz, m.dkez))
+            sums.append(w[m.dkbz - g.dkbz:m.dkez - g.dkbz].sum())
+        assert rows == list(range(g.dkbz, g.dkez))
+        assert max(sums) - w.sum() / world <= w.max() + 1e-9
+        # the unweighted cut puts more cost on the ranks that own the high wavenumbers
+        sums0 = []
+        for r in range(world):
+            m = shard.shard_wavegrid(g, r, world)
+            sums0.append(w[m.dkbz - g.dkbz:m.dkez - g.dkbz].sum())
+        assert max(sums) <= max(sums0) + 1e-9
