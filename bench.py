@@ -311,7 +311,8 @@ def base_line(args, wl, world):
     if world == 1:
         part = "one rank owns the whole wave space"
     elif sharded:
-        part = (f"ONE grid sharded over {world} ranks by contiguous kz blocks balanced on active pencils "
+        part = (f"ONE grid sharded over {world} ranks by contiguous kz blocks balanced on "
+                f"{'measured row cost' if args.balance == 'cost' else 'active pencils'} "
                 f"(whole wall-normal pencils per rank), no collective inside L; per SMR91 step one ncclAllReduce(SUM) "
                 f"of the 42 x Ny reference profiles and one ncclAllReduce(MIN) of 12 step-size candidates")
     else:
