@@ -195,6 +195,17 @@ __device__ __forceinline__ cplx ldcg_c(const cplx *p)
 }
 
 // coefficient points y0 .. y0 + ny - 1, all threads of the caller's group
+// D = A B + C on the FP64 tensor cores (DMMA.8x8x4): A 8 x 4 (lane: row lane / 4, k lane % 4), B 4 x 8 (k lane % 4,
+// column lane / 4), C / D 8 x 8 (row lane / 4, columns 2 (lane % 4), 2 (lane % 4) + 1).
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double neg_if(double v, unsigned signmask)
+{
+    return __hiloint2double(__double2hiint(v) ^ (int) signmask, __double2loint(v));
+}
+
 template <class W, class SM>
 __device__ __forceinline__ void compute_coef_range(const PackArgs &A, const SM &S, int y0, int ny, int t0, int nt)
 {
@@ -416,6 +427,7 @@ invert_sync_kernel(const PipeArgs A)
 
     for (int t = tid; t < MAXTERMS; t += W::NTH) S.tref[t] = K.terms->ref[t];
     for (int t = tid; t <= NBLOCK; t += W::NTH) S.tblk[t] = K.terms->blk_begin[t];
+    if (tid == 0) S.tbm[P] = 0.0;                                   // the padding of the DMMA fragments
     if (tid == NT) {
         for (int b = 0; b < W::NB; ++b) mbar_init(S.mbar + b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -589,6 +601,66 @@ invert_sync_kernel(const PipeArgs A)
                 bar_sync_n<BAR_ALL>(NT);
             }
             ju = max(ju, juc);
+#ifdef SZB_SYNC_U_DMMA
+            // (experiment, make XDEFS=-DSZB_SYNC_U_DMMA: correct, 20.3 ms against 19.4 ms -- the 8-byte fragment loads cost more
+            // shared-memory wavefronts than the scalar update's broadcast loads; see tools/experiments/README.md)
+            // ---------------- P3: U(t) on the FP64 tensor cores.  The rank-5 complex update of the trailing block
+            // (rows at positions 5..RW and the right-hand side, columns j+5..ju) is the real product
+            //   [C^T re | C^T im] += [U^T re | U^T im] (8 columns x 10, padded to 12) . B (12 x 8 = 4 rows x {re, im})
+            // with B = [-L re, -L im ; +L im, -L re]: one DMMA.8x8x4 chain of three per tile of 8 columns x 4 rows,
+            // a lane owning exactly one complex window element (column 8 mt + lane / 4, row 4 nt + lane % 4).  The
+            // tiles are dealt to the warps in contiguous runs of the (column tile, row tile) order, so the U^T
+            // fragments are loaded once per run.  Same FMAs as the scalar update, an eighth of the instructions.
+            {
+                constexpr int NNT = (W::NR + 3) / 4;                        // row tiles
+                constexpr unsigned ROWB = CW * sizeof(cplx);
+                const int g = lane >> 2, qd = lane & 3, part = g & 1, gr = g >> 1;
+                const unsigned char *const prow = reinterpret_cast<const unsigned char *>(S.win + (size_t) jr * CW);
+                const unsigned char *const zerop = reinterpret_cast<const unsigned char *>(S.tbm + P);   // a 0.0
+                const unsigned char *const lpb = reinterpret_cast<const unsigned char *>(S.lp);
+                // K index kk = 4 s + lane % 4: U row kk % 5, real part for kk < 5, imaginary for 5 <= kk < 10, zero beyond
+                const unsigned ao0 = qd * ROWB, ao1 = qd == 0 ? 4 * ROWB : (qd - 1) * ROWB + 8, ao2 = (qd + 3) * ROWB + 8;
+                const bool kz = qd >= 2;                                    // kk = 10, 11 in the third step
+                // B: column 2 r' + part of the tile is the real (part 0) or imaginary (part 1) part of window row r'
+                const unsigned bo0 = (gr * P + qd) * 16 + 8 * part;
+                const unsigned bo1 = qd == 0 ? (gr * P + 4) * 16 + 8 * part : (gr * P + qd - 1) * 16 + 8 * (1 - part);
+                const unsigned bo2 = (gr * P + qd + 3) * 16 + 8 * (1 - part);
+                const unsigned ng1 = (qd == 0 || part) ? 0x80000000u : 0u, ng2 = part ? 0x80000000u : 0u;
+                const int nmt = (ncols + 7) >> 3, ntl = nmt * NNT;
+                int id = (warp * ntl) / NWC;
+                const int idh = ((warp + 1) * ntl) / NWC;
+                int mt = id / NNT, nt = id - mt * NNT;
+                while (id < idh) {
+                    const int i = 8 * mt + g;
+                    int c = jc + P + i; if (c >= CW) c -= CW;
+                    const bool cv = i < ncols;
+                    if (!cv) c = jc;
+                    const unsigned char *const colp = prow + 16 * c;
+                    const double a0 = *reinterpret_cast<const double *>(colp + ao0);
+                    const double a1 = *reinterpret_cast<const double *>(colp + ao1);
+                    const double a2 = *reinterpret_cast<const double *>(kz ? zerop : colp + ao2);
+                    const int nte = min(NNT, nt + (idh - id));
+                    id += nte - nt;
+#pragma unroll 2
+                    for (; nt < nte; ++nt) {
+                        const int pos = P + 4 * nt + qd;
+                        int slot = RW;
+                        if (pos < RW) { slot = jr + pos; if (slot >= RW) slot -= RW; }
+                        cplx *const cp = S.win + (size_t) slot * CW + c;
+                        const unsigned char *const bb = lpb + (P + 4 * nt) * P * 16;
+                        const double b0 = neg_if(*reinterpret_cast<const double *>(bb + bo0), 0x80000000u);
+                        const double b1 = neg_if(*reinterpret_cast<const double *>(bb + bo1), ng1);
+                        const double b2 = neg_if(*reinterpret_cast<const double *>(kz ? zerop : bb + bo2), ng2);
+                        cplx w = *cp;
+                        dmma884(w.x, w.y, a0, b0);
+                        dmma884(w.x, w.y, a1, b1);
+                        dmma884(w.x, w.y, a2, b2);
+                        if (cv && pos <= RW) *cp = w;
+                    }
+                    nt = 0; ++mt;
+                }
+            }
+#else
             // ---------------- P3: U(t): trailing columns j+5 .. ju, warp = columns (cyclically), lane = row.
             // Column indices past the last one are pointed at the retired column slot jc: dead data.
             // Explicit shared-memory addresses and loads in program order: every pivot-row operand is
@@ -651,6 +723,7 @@ invert_sync_kernel(const PipeArgs A)
                     }
                 }
             }
+#endif
             SPROF_MARK(4);
             bar_sync_n<BAR_ALL>(NT);
             SPROF_MARK(5);
