@@ -44,6 +44,15 @@
 
 #include "invert_fused.cuh"
 
+// Experiment switches (tools/experiments/README.md): columns per warp pass of the trailing update, and how many of
+// its last columns are left to the assembly warps of the next P1 (measured: 5 / 0 is the fastest).
+#ifndef SZB_SYNC_NCH
+#define SZB_SYNC_NCH 5
+#endif
+#ifndef SZB_SYNC_NDEF
+#define SZB_SYNC_NDEF 0
+#endif
+
 // Optional phase timing (make PROF=1): per-phase clock64() deltas of thread 0 (panel warp 0) in
 // slots 0..6 and of the first thread of the first non-panel warp in slots 8..14, summed over all
 // pencils and CTAs; slot 7 counts exact-path panels, slot 15 all panels.  szb_debug_sync_prof().
@@ -92,7 +101,8 @@ struct SyncCfg {
     static constexpr int LDMAX = 17;                // >= ld of the B-spline operators (2k - 3 <= 17)
     static constexpr int NWC = 7;                   // compute warps; warp NWC is the solver warp
     static constexpr int NT = 32 * NWC, NTH = NT + 32;
-    static constexpr int NCH = 5;                   // trailing columns a warp updates at once
+    static constexpr int NCH = SZB_SYNC_NCH;        // trailing columns a warp updates at once in P3
+    static constexpr int NDEF = SZB_SYNC_NDEF;      // trailing columns left to the assembly warps of the next P1 (0: none)
     static constexpr int NR = RW - P + 1;           // rows of the trailing update (incl. the right-hand side)
     static constexpr int NMAIN = NR < 32 ? NR : 32, NTAIL = NR - NMAIN;
     static constexpr int CH = 4, NB = 2;            // solver: L columns per TMA chunk, ring depth
@@ -168,7 +178,7 @@ __device__ __forceinline__ SSmem<W> sync_carve(unsigned char *raw)
     return S;
 }
 
-constexpr int BAR_ALL = 1, BAR_PP = 7;
+constexpr int BAR_ALL = 1, BAR_ASM = 6, BAR_PP = 7;
 
 // barrier BAR_ALL of `count` threads that also ORs a predicate over them
 __device__ __forceinline__ int bar_red_or(int pred, int count)
@@ -334,6 +344,74 @@ __device__ __forceinline__ void urows_column(const SM &S, int jr, int cs, cplx *
 #pragma unroll
         for (int i2 = 0; i2 < k; ++i2) submul(u[k], S.lp[k * P + i2], u[i2]);
         pc[k * CW] = u[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// U(t): rank-5 update of trailing columns i = i0, i0 + istep, ... < ilim (column j + 5 + i of the matrix), NCHX of them
+// at once, lane = row.  Column indices past the last one are pointed at the retired column slot jc: dead data.
+// Explicit shared-memory addresses and loads in program order: every pivot-row operand is re-loaded right after
+// its use, four complex updates ahead of the next one (the compiler's own schedule went column by column, a chain
+// of ten dependent FMAs behind each load).
+// ---------------------------------------------------------------------------------------------
+template <class W, int NCHX, class SM>
+__device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, int istep, int ilim, int lane)
+{
+    constexpr int RW = W::RW, CW = W::CW;
+    const int pos = P + lane;                                   // main rows: positions 5 .. 5 + NMAIN - 1
+    int rslot = RW;
+    if (pos < RW) { rslot = jr + pos; if (rslot >= RW) rslot -= RW; }
+    const unsigned lrow_sa = smem_u32(S.lp + (lane < W::NMAIN ? pos : P) * P);      // this lane's multipliers
+    const unsigned prow_sa = smem_u32(S.win + (size_t) jr * CW);    // the five pivot rows (rows of U now)
+    const unsigned dro = (unsigned) ((rslot - jr) * CW * (int) sizeof(cplx));   // this lane's row relative to them
+    constexpr unsigned ROWB = CW * sizeof(cplx);
+    for (int m0 = 0; i0 + istep * m0 < ilim; m0 += NCHX) {
+        unsigned ca[NCHX];
+#pragma unroll
+        for (int x = 0; x < NCHX; ++x) {
+            const int i = i0 + istep * (m0 + x);
+            int c = jc + P + i; if (c >= CW) c -= CW;
+            ca[x] = prow_sa + 16u * (unsigned) (i < ilim ? c : jc);
+        }
+        if (lane < W::NMAIN) {
+            cplx w[NCHX], u[NCHX];
+            cplx lk = lds_cv(lrow_sa);
+#pragma unroll
+            for (int x = 0; x < NCHX; ++x) u[x] = lds_cv(ca[x]);
+#pragma unroll
+            for (int x = 0; x < NCHX; ++x) w[x] = lds_cv(ca[x] + dro);
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                cplx ln = lk;
+                if (k + 1 < P) ln = lds_cv(lrow_sa + 16 * (k + 1));
+#pragma unroll
+                for (int x = 0; x < NCHX; ++x) {
+                    submul(w[x], lk, u[x]);
+                    if (k + 1 < P) u[x] = lds_cv(ca[x] + (k + 1) * ROWB);
+                }
+                lk = ln;
+            }
+#pragma unroll
+            for (int x = 0; x < NCHX; ++x) sts_if(ca[x] + dro, w[x], true);
+        }
+        // tail rows (positions 5 + NMAIN .. RW): one element per lane
+        for (int e = lane; e < W::NTAIL * NCHX; e += 32) {
+            const int x = e / (W::NTAIL > 0 ? W::NTAIL : 1), r = e - x * W::NTAIL;
+            const int i = i0 + istep * (m0 + x);
+            int c = jc + P + i; if (c >= CW) c -= CW;
+            if (i >= ilim) c = jc;
+            const int tp = P + W::NMAIN + r;
+            int ts = RW;
+            if (tp < RW) { ts = jr + tp; if (ts >= RW) ts -= RW; }
+            const unsigned pu = prow_sa + 16u * (unsigned) c, pw = smem_u32(S.win + (size_t) ts * CW + c);
+            const unsigned pl = smem_u32(S.lp + tp * P);
+            cplx w = lds_c(pw), uu[P], ll[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) { uu[k] = lds_c(pu + k * ROWB); ll[k] = lds_c(pl + 16 * k); }
+#pragma unroll
+            for (int k = 0; k < P; ++k) submul(w, ll[k], uu[k]);
+            sts_if(pw, w, true);
+        }
     }
 }
 
@@ -516,6 +594,14 @@ invert_sync_kernel(const PipeArgs A)
                 const int yI = (j - P + RW) / P;
                 int jro = jr - P; if (jro < 0) jro += RW;
                 int jco = jc - P; if (jco < 0) jco += CW;
+                if (W::NDEF > 0) {
+                    // the last columns of U(t-1), then (all of them done) the retired pivot rows may be overwritten
+                    const int ncp = min(ju, N - 1) - j + 1;
+                    if (ncp >= W::NDEF + 2 * P) {
+                        u_columns<W, 1>(S, jro, jco, ncp - W::NDEF + warp - 1, NWC - 1, ncp, lane);
+                        bar_sync_n<BAR_ASM>(NTA);
+                    }
+                }
                 cplx *dst = S.win + (size_t) jro * CW;
                 if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
                     assemble_block_interior<W>(K, S, S.drow, yI, dst, ta, NTA);
@@ -661,67 +747,11 @@ invert_sync_kernel(const PipeArgs A)
                 }
             }
 #else
-            // ---------------- P3: U(t): trailing columns j+5 .. ju, warp = columns (cyclically), lane = row.
-            // Column indices past the last one are pointed at the retired column slot jc: dead data.
-            // Explicit shared-memory addresses and loads in program order: every pivot-row operand is
-            // re-loaded right after its use, four complex updates ahead of the next one (the compiler's own
-            // schedule went column by column, a chain of ten dependent FMAs behind each load). ----------------
+            // ---------------- P3: U(t): trailing columns j+5 .. ju, warp = columns (cyclically), lane = row.  The last
+            // ND columns are left to the assembly warps of the next P1, which would otherwise wait for F1(t+1). ----------------
             {
-                const int pos = P + lane;                                   // main rows: positions 5 .. 5 + NMAIN - 1
-                int rslot = RW;
-                if (pos < RW) { rslot = jr + pos; if (rslot >= RW) rslot -= RW; }
-                const unsigned lrow_sa = smem_u32(S.lp + (lane < W::NMAIN ? pos : P) * P);      // this lane's multipliers
-                const unsigned prow_sa = smem_u32(S.win + (size_t) jr * CW);    // the five pivot rows (rows of U now)
-                const unsigned dro = (unsigned) ((rslot - jr) * CW * (int) sizeof(cplx));   // this lane's row relative to them
-                constexpr unsigned ROWB = CW * sizeof(cplx);
-                for (int m0 = 0; warp + NWC * m0 < ncols; m0 += NCH) {
-                    unsigned ca[NCH];
-#pragma unroll
-                    for (int x = 0; x < NCH; ++x) {
-                        const int i = warp + NWC * (m0 + x);
-                        int c = jc + P + i; if (c >= CW) c -= CW;
-                        ca[x] = prow_sa + 16u * (unsigned) (i < ncols ? c : jc);
-                    }
-                    if (lane < W::NMAIN) {
-                        cplx w[NCH], u[NCH];
-                        cplx lk = lds_cv(lrow_sa);
-#pragma unroll
-                        for (int x = 0; x < NCH; ++x) u[x] = lds_cv(ca[x]);
-#pragma unroll
-                        for (int x = 0; x < NCH; ++x) w[x] = lds_cv(ca[x] + dro);
-#pragma unroll
-                        for (int k = 0; k < P; ++k) {
-                            cplx ln = lk;
-                            if (k + 1 < P) ln = lds_cv(lrow_sa + 16 * (k + 1));
-#pragma unroll
-                            for (int x = 0; x < NCH; ++x) {
-                                submul(w[x], lk, u[x]);
-                                if (k + 1 < P) u[x] = lds_cv(ca[x] + (k + 1) * ROWB);
-                            }
-                            lk = ln;
-                        }
-#pragma unroll
-                        for (int x = 0; x < NCH; ++x) sts_if(ca[x] + dro, w[x], true);
-                    }
-                    // tail rows (positions 5 + NMAIN .. RW): one element per lane
-                    for (int e = lane; e < W::NTAIL * NCH; e += 32) {
-                        const int x = e / (W::NTAIL > 0 ? W::NTAIL : 1), r = e - x * W::NTAIL;
-                        const int i = warp + NWC * (m0 + x);
-                        int c = jc + P + i; if (c >= CW) c -= CW;
-                        if (i >= ncols) c = jc;
-                        const int tp = P + W::NMAIN + r;
-                        int ts = RW;
-                        if (tp < RW) { ts = jr + tp; if (ts >= RW) ts -= RW; }
-                        const unsigned pu = prow_sa + 16u * (unsigned) c, pw = smem_u32(S.win + (size_t) ts * CW + c);
-                        const unsigned pl = smem_u32(S.lp + tp * P);
-                        cplx w = lds_c(pw), uu[P], ll[P];
-#pragma unroll
-                        for (int k = 0; k < P; ++k) { uu[k] = lds_c(pu + k * ROWB); ll[k] = lds_c(pl + 16 * k); }
-#pragma unroll
-                        for (int k = 0; k < P; ++k) submul(w, ll[k], uu[k]);
-                        sts_if(pw, w, true);
-                    }
-                }
+                const int nd = ncols >= W::NDEF + 2 * P ? W::NDEF : 0;
+                u_columns<W, NCH>(S, jr, jc, warp, NWC, ncols - nd, lane);
             }
 #endif
             SPROF_MARK(4);

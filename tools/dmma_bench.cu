@@ -66,6 +66,47 @@ void run(const char *name, double flop_per_op, double *out, long long *clk, int 
            cudaGetErrorString(cudaGetLastError()));
 }
 
+// warps with odd index run DFMAs, even ones DMMAs: do the two share a pipe?
+__global__ void __launch_bounds__(256, 3) mixed(double *out, int iters, int mode)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = 1e-3 * (lane + i); c[i][1] = 2e-3 * (lane - i); }
+    const double a = 1.0 + 1e-9 * lane, b = 1e-6 * lane;
+    const bool dm = mode == 1 || (mode == 2 && (warp & 1) == 0);
+    if (dm) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+        }
+    } else {
+        for (int it = 0; it < iters * 4; ++it) {      // 4 x 16 DFMA = the lane-FMAs of 8 DMMAs
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i][0] = fma(a, b, c[i][0]); c[i][1] = fma(a, b, c[i][1]); }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+void run_mixed(double *out)
+{
+    const int iters = 20000;
+    for (int mode = 0; mode < 3; ++mode) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        mixed<<<148 * 3, 256>>>(out, 100, mode);
+        cudaEventRecord(e0);
+        mixed<<<148 * 3, 256>>>(out, iters, mode);
+        cudaEventRecord(e1); cudaDeviceSynchronize();
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = (double) iters * 8 * 512 * 148 * 3 * 8;       // every warp does the same number of flops
+        printf("mixed mode %d (0 all DFMA, 1 all DMMA, 2 half / half): %.3f ms  %.2f TFLOP/s\n", mode, ms, flop / (ms * 1e-3) / 1e12);
+    }
+}
+
 int main()
 {
     double *out; long long *clk;
@@ -88,5 +129,6 @@ int main()
     }
     run<1, 2>("m8n8k4", 2 * 8 * 8 * 4, out, clk, 3, 8);
     run<3, 2>("m16n8k8", 2 * 16 * 8 * 8, out, clk, 3, 8);
+    run_mixed(out);
     return 0;
 }
