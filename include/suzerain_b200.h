@@ -108,6 +108,17 @@ int szb_bsplineop_accumulate_complex_batch(const szb_bsplineop *w, int d, int nr
         const double alpha[2], const szb_complex *d_x, size_t ldx,
         const double beta[2],        szb_complex *d_y, size_t ldy, void *stream);
 
+/* The other three members of the family (suzerain/bsplineop.h:246-295, 360-367; bsplineop.c:222-258, 299-381), same
+ * batching: x <- alpha D^(d) x in place for complex and for real pencils (the reference's scratch copy is the
+ * kernel's staging buffer) and y <- alpha D^(d) x + beta y for real pencils.  alpha and beta are real here, as in
+ * the reference.  Return values follow the argument positions of the complex call. */
+int szb_bsplineop_apply_complex_batch(const szb_bsplineop *w, int d, int nrhs, double alpha,
+        szb_complex *d_x, size_t ldx, void *stream);
+int szb_bsplineop_accumulate_batch(const szb_bsplineop *w, int d, int nrhs, double alpha,
+        const double *d_x, size_t ldx, double beta, double *d_y, size_t ldy, void *stream);
+int szb_bsplineop_apply_batch(const szb_bsplineop *w, int d, int nrhs, double alpha,
+        double *d_x, size_t ldx, void *stream);
+
 /* ------------------------------------------------------------------------ *
  * Linearised perfect-gas operator (M + phi L).  Replaces
  * suzerain/rholut_imexop.h:66-469.  Struct layouts are field-for-field those

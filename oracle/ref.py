@@ -267,6 +267,24 @@ class Problem:
                                                out.ctypes.data_as(C.c_void_p), 1, n, C.byref(self.w))
         return out
 
+    def bsplineop_accumulate(self, d, alpha: float, x, beta: float = 0.0, y=None):
+        """Real coefficients: suzerain_bsplineop_accumulate (suzerain/bsplineop.c:222-258)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nrhs, n = x.shape
+        out = (np.zeros_like(x) if y is None else np.array(y, dtype=np.float64, order="C", copy=True))
+        lib().ref_bsplineop_accumulate(int(d), int(nrhs), C.c_double(alpha), x.ctypes.data_as(C.c_void_p), 1, n,
+                                       C.c_double(beta), out.ctypes.data_as(C.c_void_p), 1, n, C.byref(self.w))
+        return out
+
+    def bsplineop_apply(self, d, alpha: float, x):
+        """In place, real or complex rows: suzerain_bsplineop_apply / _apply_complex (suzerain/bsplineop.c:299-381)."""
+        cplx = np.iscomplexobj(x)
+        out = np.array(x, dtype=np.complex128 if cplx else np.float64, order="C", copy=True)
+        nrhs, n = out.shape
+        f = lib().ref_bsplineop_apply_complex if cplx else lib().ref_bsplineop_apply
+        f(int(d), int(nrhs), C.c_double(alpha), out.ctypes.data_as(C.c_void_p), 1, n, C.byref(self.w))
+        return out
+
 
 def zgbsv_T(N, KL, KU, LU, B):
     """In-place zgbtrf + zgbtrs('T') on LAPACK band storage.

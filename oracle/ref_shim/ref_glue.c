@@ -408,6 +408,44 @@ void ref_bsplineop_accumulate_complex(int nderiv, int nrhs, const double alpha[2
                                 x + (size_t) j * ldx, incx, b, y + (size_t) j * ldy, incy);
 }
 
+/* suzerain_bsplineop_accumulate (suzerain/bsplineop.c:222-258), suzerain_bsplineop_apply (:299-337) and
+ * suzerain_bsplineop_apply_complex (:339-381) restated the same way around the reference's own
+ * suzerain_blas_dgbmv / suzerain_blas_dcopy: real coefficients, and the in-place forms (a scratch copy of each
+ * vector; real and imaginary parts separately with stride 2 for the complex one). */
+void ref_bsplineop_accumulate(int nderiv, int nrhs, double alpha, const double *x, int incx, int ldx,
+        double beta, double *y, int incy, int ldy, const suzerain_bsplineop_workspace *w)
+{
+    for (int j = 0; j < nrhs; ++j)
+        suzerain_blas_dgbmv('T', w->n, w->n, w->kl[nderiv], w->ku[nderiv], alpha, w->D_T[nderiv], w->ld,
+                            x + (size_t) j * ldx, incx, beta, y + (size_t) j * ldy, incy);
+}
+void ref_bsplineop_apply(int nderiv, int nrhs, double alpha, double *x, int incx, int ldx,
+        const suzerain_bsplineop_workspace *w)
+{
+    double *scratch = suzerain_blas_malloc(w->n * sizeof(double));
+    for (int j = 0; j < nrhs; ++j) {
+        double *x_j = x + (size_t) j * ldx;
+        suzerain_blas_dcopy(w->n, x_j, incx, scratch, 1);
+        suzerain_blas_dgbmv('T', w->n, w->n, w->kl[nderiv], w->ku[nderiv], alpha, w->D_T[nderiv], w->ld,
+                            scratch, 1, 0.0, x_j, incx);
+    }
+    suzerain_blas_free(scratch);
+}
+void ref_bsplineop_apply_complex(int nderiv, int nrhs, double alpha, complex_double *x, int incx, int ldx,
+        const suzerain_bsplineop_workspace *w)
+{
+    double *scratch = suzerain_blas_malloc(w->n * sizeof(double));
+    for (int j = 0; j < nrhs; ++j) {
+        double *xreal_j = (double *) (x + (size_t) j * ldx);
+        for (int c = 0; c < 2; ++c) {
+            suzerain_blas_dcopy(w->n, xreal_j + c, 2 * incx, scratch, 1);
+            suzerain_blas_dgbmv('T', w->n, w->n, w->kl[nderiv], w->ku[nderiv], alpha, w->D_T[nderiv], w->ld,
+                                scratch, 1, 0.0, xreal_j + c, 2 * incx);
+        }
+    }
+    suzerain_blas_free(scratch);
+}
+
 /* by-pointer wrappers: ctypes cannot pass C99 complex by value */
 void suzerain_diffwave_apply(int, int, complex_double, complex_double *, double, double, int,
                              int, int, int, int, int, int, int, int);

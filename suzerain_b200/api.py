@@ -360,6 +360,32 @@ def bsplineop_accumulate_complex_batch(bop, d, alpha, x, beta, y, stream=None):
     return y
 
 
+def bsplineop_accumulate_batch(bop, d, alpha, x, beta, y, stream=None):
+    """Real pencils: y <- alpha D^(d) x + beta y over the rows of the float64 device tensors x, y (nrhs, n):
+    suzerain_bsplineop_accumulate (suzerain/bsplineop.c:222-258)."""
+    import torch
+    assert x.is_cuda and y.is_cuda and x.dtype == torch.float64 and y.dtype == torch.float64
+    st = stream or torch.cuda.current_stream(x.device)
+    rc = _L.load().szb_bsplineop_accumulate_batch(
+        bop.handle, int(d), int(x.shape[0]), float(alpha), C.c_void_p(x.data_ptr()), x.stride(0), float(beta),
+        C.c_void_p(y.data_ptr()), y.stride(0), C.c_void_p(st.cuda_stream))
+    _L.check("szb_bsplineop_accumulate_batch", rc)
+    return y
+
+
+def bsplineop_apply_batch(bop, d, alpha, x, stream=None):
+    """In place: x <- alpha D^(d) x over the rows of the device tensor x (nrhs, n), float64 or complex128:
+    suzerain_bsplineop_apply / suzerain_bsplineop_apply_complex (suzerain/bsplineop.c:299-381)."""
+    import torch
+    assert x.is_cuda and x.dtype in (torch.float64, torch.complex128)
+    st = stream or torch.cuda.current_stream(x.device)
+    name = "szb_bsplineop_apply_complex_batch" if x.dtype == torch.complex128 else "szb_bsplineop_apply_batch"
+    rc = getattr(_L.load(), name)(bop.handle, int(d), int(x.shape[0]), float(alpha), C.c_void_p(x.data_ptr()),
+                                  x.stride(0), C.c_void_p(st.cuda_stream))
+    _L.check(name, rc)
+    return x
+
+
 def diffwave_apply(dxcnt, dzcnt, alpha, x, grid, stream=None):
     """x <- alpha (i kx)^dxcnt (i kz)^dzcnt x in place on the device tensor x (nz, nx, Ny):
     suzerain_diffwave_apply (suzerain/diffwave.c:65-129)."""

@@ -85,6 +85,48 @@ bop_accumulate_kernel(const BopArgs A)
     }
 }
 
+// The same for real coefficients (suzerain_bsplineop_accumulate / _apply, suzerain/bsplineop.c:222-258, 299-337).
+// Pencils of n doubles need not be 16-byte aligned, so the group is staged with plain coalesced loads instead of
+// TMA bulk copies; a group is read completely before any of it is written, which makes x == y (in place) safe.
+struct BopRealArgs {
+    const double *Dr;
+    int n, kl, ku, ld, nrhs, group, nthr;
+    double alpha, beta;
+    const double *x; size_t ldx;
+    double *y; size_t ldy;
+};
+
+__global__ void __launch_bounds__(512)
+bop_real_kernel(const BopRealArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = A.n, np = n + A.kl + A.ku, G = A.group;
+    double *s_x = reinterpret_cast<double *>(smem_raw);            // [G][ku + n + kl], zero halo
+    for (int e = threadIdx.x; e < G * np; e += blockDim.x) s_x[e] = 0.0;
+    __syncthreads();
+    const int q = threadIdx.x / A.nthr, i = threadIdx.x - q * A.nthr;
+    const int ngroups = (A.nrhs + G - 1) / G;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int rhs = g * G + q;
+        const bool live = i < n && rhs < A.nrhs;
+        double yold = 0.0;
+        if (live) {
+            s_x[q * np + A.ku + i] = A.x[(size_t) rhs * A.ldx + i];
+            if (A.beta != 0.0) yold = A.y[(size_t) rhs * A.ldy + i];
+        }
+        __syncthreads();
+        if (live) {
+            const double *xs = s_x + q * np + i;
+            const double *D = A.Dr + i;
+            double s = 0.0;
+#pragma unroll 4
+            for (int r = 0; r < A.ld; ++r) s = fma(xs[r], __ldg(D + (size_t) r * n), s);
+            A.y[(size_t) rhs * A.ldy + i] = A.beta != 0.0 ? A.alpha * s + A.beta * yold : A.alpha * s;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // diffwave
 // ------------------------------------------------------------------------------------------
@@ -169,6 +211,80 @@ using namespace szb;
 
 extern "C" {
 
+// device copy of all operators, r-major with the common (max) bandwidths:
+// Dr[(d*ld + r)*n + i] = D^(d)[i, i - ku + r]; made once per device
+static int bop_upload(const szb_bsplineop *w, int dev)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (w->d_Dr && w->d_dev != dev) { cudaFree(w->d_Dr); w->d_Dr = nullptr; }
+    if (!w->d_Dr) {
+        const int n = w->n, ld = w->ld;
+        std::vector<double> h((size_t) (w->nderiv + 1) * ld * n);
+        for (int dd = 0; dd <= w->nderiv; ++dd) {
+            const double *blk = w->storage.data() + (size_t) dd * ld * n;
+            for (int i = 0; i < n; ++i)
+                for (int r = 0; r < ld; ++r) h[((size_t) dd * ld + r) * n + i] = blk[(size_t) i * ld + r];
+        }
+        SZB_CUDA_OK(cudaMalloc(&w->d_Dr, h.size() * sizeof(double)));
+        SZB_CUDA_OK(cudaMemcpy(w->d_Dr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        w->d_dev = dev;
+    }
+    return 0;
+}
+
+static int bop_complex_launch(const szb_bsplineop *w, int d, int nrhs, cplx alpha, const szb_complex *d_x, size_t ldx,
+                              cplx beta, szb_complex *d_y, size_t ldy, void *stream)
+{
+    int dev = 0;
+    SZB_CUDA_OK(cudaGetDevice(&dev));
+    if (int rc = bop_upload(w, dev)) return rc;
+    BopArgs A;
+    A.Dr = w->d_Dr + (size_t) d * w->ld * w->n;
+    A.n = w->n; A.kl = w->max_kl; A.ku = w->max_ku; A.ld = w->ld; A.nrhs = nrhs;
+    A.nthr = (w->n + 31) / 32 * 32;
+    if (A.nthr > 512) return -1;
+    A.group = std::max(1, 384 / A.nthr);
+    A.alpha = alpha; A.beta = beta;
+    A.x = reinterpret_cast<const cplx *>(d_x); A.ldx = ldx;
+    A.y = reinterpret_cast<cplx *>(d_y); A.ldy = ldy;
+    const size_t smem = sizeof(cplx) * BOP_STAGES * (size_t) A.group * (A.n + A.kl + A.ku);
+    if (smem > 48 * 1024)
+        SZB_CUDA_OK(cudaFuncSetAttribute(bop_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ngroups = (nrhs + A.group - 1) / A.group;
+    bop_accumulate_kernel<<<std::min(ngroups, 4 * sms), A.group * A.nthr, smem, (cudaStream_t) stream>>>(A);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int bop_real_launch(const szb_bsplineop *w, int d, int nrhs, double alpha, const double *d_x, size_t ldx,
+                           double beta, double *d_y, size_t ldy, void *stream)
+{
+    int dev = 0;
+    SZB_CUDA_OK(cudaGetDevice(&dev));
+    if (int rc = bop_upload(w, dev)) return rc;
+    BopRealArgs A;
+    A.Dr = w->d_Dr + (size_t) d * w->ld * w->n;
+    A.n = w->n; A.kl = w->max_kl; A.ku = w->max_ku; A.ld = w->ld; A.nrhs = nrhs;
+    A.nthr = (w->n + 31) / 32 * 32;
+    if (A.nthr > 512) return -1;
+    A.group = std::max(1, 512 / A.nthr);
+    A.alpha = alpha; A.beta = beta;
+    A.x = d_x; A.ldx = ldx; A.y = d_y; A.ldy = ldy;
+    const size_t smem = sizeof(double) * (size_t) A.group * (A.n + A.kl + A.ku);
+    if (smem > 48 * 1024)
+        SZB_CUDA_OK(cudaFuncSetAttribute(bop_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ngroups = (nrhs + A.group - 1) / A.group;
+    bop_real_kernel<<<std::min(ngroups, 4 * sms), A.group * A.nthr, smem, (cudaStream_t) stream>>>(A);
+    count_launch();
+    SZB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int szb_bsplineop_accumulate_complex_batch(const szb_bsplineop *w, int d, int nrhs,
         const double alpha[2], const szb_complex *d_x, size_t ldx,
         const double beta[2], szb_complex *d_y, size_t ldy, void *stream)
@@ -184,45 +300,48 @@ int szb_bsplineop_accumulate_complex_batch(const szb_bsplineop *w, int d, int nr
     if (ldy < (size_t) w->n) return -9;
     if ((const void *) d_x == (const void *) d_y) return -8;        // bsplineop.c:283-286
     if (nrhs == 0) return 0;
-    int dev = 0;
-    SZB_CUDA_OK(cudaGetDevice(&dev));
-    {
-        // device copy of all operators, r-major with the common (max) bandwidths:
-        // Dr[(d*ld + r)*n + i] = D^(d)[i, i - ku + r]; made once per device
-        std::lock_guard<std::mutex> lock(g_mutex);
-        if (w->d_Dr && w->d_dev != dev) { cudaFree(w->d_Dr); w->d_Dr = nullptr; }
-        if (!w->d_Dr) {
-            const int n = w->n, ld = w->ld;
-            std::vector<double> h((size_t) (w->nderiv + 1) * ld * n);
-            for (int dd = 0; dd <= w->nderiv; ++dd) {
-                const double *blk = w->storage.data() + (size_t) dd * ld * n;
-                for (int i = 0; i < n; ++i)
-                    for (int r = 0; r < ld; ++r) h[((size_t) dd * ld + r) * n + i] = blk[(size_t) i * ld + r];
-            }
-            SZB_CUDA_OK(cudaMalloc(&w->d_Dr, h.size() * sizeof(double)));
-            SZB_CUDA_OK(cudaMemcpy(w->d_Dr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
-            w->d_dev = dev;
-        }
-    }
-    BopArgs A;
-    A.Dr = w->d_Dr + (size_t) d * w->ld * w->n;
-    A.n = w->n; A.kl = w->max_kl; A.ku = w->max_ku; A.ld = w->ld; A.nrhs = nrhs;
-    A.nthr = (w->n + 31) / 32 * 32;
-    if (A.nthr > 512) return -1;
-    A.group = std::max(1, 384 / A.nthr);
-    A.alpha = cplx(alpha[0], alpha[1]); A.beta = cplx(beta[0], beta[1]);
-    A.x = reinterpret_cast<const cplx *>(d_x); A.ldx = ldx;
-    A.y = reinterpret_cast<cplx *>(d_y); A.ldy = ldy;
-    const size_t smem = sizeof(cplx) * BOP_STAGES * (size_t) A.group * (A.n + A.kl + A.ku);
-    if (smem > 48 * 1024)
-        SZB_CUDA_OK(cudaFuncSetAttribute(bop_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ngroups = (nrhs + A.group - 1) / A.group;
-    bop_accumulate_kernel<<<std::min(ngroups, 4 * sms), A.group * A.nthr, smem, (cudaStream_t) stream>>>(A);
-    count_launch();
-    SZB_CUDA_OK(cudaGetLastError());
-    return 0;
+    return bop_complex_launch(w, d, nrhs, cplx(alpha[0], alpha[1]), d_x, ldx, cplx(beta[0], beta[1]), d_y, ldy, stream);
+}
+
+int szb_bsplineop_apply_complex_batch(const szb_bsplineop *w, int d, int nrhs, double alpha,
+        szb_complex *d_x, size_t ldx, void *stream)
+{
+    if (!w) return -1;
+    if (d < 0 || d > w->nderiv) return -2;
+    if (nrhs < 0) return -3;
+    if (!d_x) return -5;
+    if (ldx < (size_t) w->n) return -6;
+    if (nrhs == 0) return 0;
+    // every pencil is in shared memory before its result is stored, so the scratch copy of the
+    // reference (bsplineop.c:356-376) is the staging buffer
+    return bop_complex_launch(w, d, nrhs, cplx(alpha, 0.0), d_x, ldx, cplx(0.0, 0.0), d_x, ldx, stream);
+}
+
+int szb_bsplineop_accumulate_batch(const szb_bsplineop *w, int d, int nrhs, double alpha,
+        const double *d_x, size_t ldx, double beta, double *d_y, size_t ldy, void *stream)
+{
+    if (!w) return -1;
+    if (d < 0 || d > w->nderiv) return -2;
+    if (nrhs < 0) return -3;
+    if (!d_x) return -5;
+    if (ldx < (size_t) w->n) return -6;
+    if (!d_y) return -8;
+    if (ldy < (size_t) w->n) return -9;
+    if ((const void *) d_x == (const void *) d_y) return -8;        // bsplineop.c:244-247
+    if (nrhs == 0) return 0;
+    return bop_real_launch(w, d, nrhs, alpha, d_x, ldx, beta, d_y, ldy, stream);
+}
+
+int szb_bsplineop_apply_batch(const szb_bsplineop *w, int d, int nrhs, double alpha,
+        double *d_x, size_t ldx, void *stream)
+{
+    if (!w) return -1;
+    if (d < 0 || d > w->nderiv) return -2;
+    if (nrhs < 0) return -3;
+    if (!d_x) return -5;
+    if (ldx < (size_t) w->n) return -6;
+    if (nrhs == 0) return 0;
+    return bop_real_launch(w, d, nrhs, alpha, d_x, ldx, 0.0, d_x, ldx, stream);
 }
 
 static int diffwave_launch(int dxcnt, int dzcnt, const double alpha[2], const szb_complex *d_x,

@@ -474,3 +474,39 @@ def test_cxx_bsmbsm_solver_protocol(dev, method, tmp_path):
     want[:, q] = X                                                             # P^T x
     assert rinfo == 0 and np.array_equal(ipiv, piv)
     assert pc.relmax(x, want) <= TOL
+
+
+# ---------------------------------------------------------------------------
+# the rest of the bsplineop apply / accumulate family: real pencils and the in-place forms
+# (suzerain/bsplineop.c:222-258, 299-381), against the reference's own dgbmv
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("k,Ny,nrhs", [(8, 96, 1000), (6, 41, 37), (4, 24, 5), (10, 64, 129)])
+def test_bsplineop_real_and_in_place_match_reference(dev, k, Ny, nrhs):
+    import torch
+    import suzerain_b200 as sz
+    case = pc.make_case("tiny_16x24x16", max_pencils=4, k=k, Ny=Ny)
+    P = pc.oracle_problem(case, "ref")
+    rng = np.random.default_rng(11)
+    xr = rng.standard_normal((nrhs, Ny)); yr = rng.standard_normal((nrhs, Ny))
+    xc = rng.standard_normal((nrhs, Ny)) + 1j * rng.standard_normal((nrhs, Ny))
+    for d in range(3):
+        for beta in (0.0, -0.6):
+            want = P.bsplineop_accumulate(d, 1.3, xr, beta, yr)
+            got = sz.bsplineop_accumulate_batch(case.bop, d, 1.3, torch.from_numpy(xr).to(dev), beta,
+                                                torch.from_numpy(yr.copy()).to(dev))
+            assert pc.relmax(got.cpu().numpy(), want) <= TOL
+        # in place, real (odd Ny: pencils that are not 16-byte aligned) and complex
+        got = sz.bsplineop_apply_batch(case.bop, d, -0.7, torch.from_numpy(xr.copy()).to(dev))
+        assert pc.relmax(got.cpu().numpy(), P.bsplineop_apply(d, -0.7, xr)) <= TOL
+        got = sz.bsplineop_apply_batch(case.bop, d, 2.5, torch.from_numpy(xc.copy()).to(dev))
+        assert pc.relmax(got.cpu().numpy(), P.bsplineop_apply(d, 2.5, xc)) <= TOL
+    # padded leading dimension: only the first Ny entries of a row are touched
+    buf = torch.full((nrhs, Ny + 3), 7.0, dtype=torch.float64, device=dev)
+    buf[:, :Ny] = torch.from_numpy(xr).to(dev)
+    sz.bsplineop_apply_batch(case.bop, 1, 1.0, buf[:, :Ny])
+    assert pc.relmax(buf[:, :Ny].cpu().numpy(), P.bsplineop_apply(1, 1.0, xr)) <= TOL
+    assert bool((buf[:, Ny:] == 7.0).all())
+    # x == y is refused by the accumulating forms, as in the reference (bsplineop.c:244-247)
+    t = torch.from_numpy(xr.copy()).to(dev)
+    with pytest.raises(Exception):
+        sz.bsplineop_accumulate_batch(case.bop, 0, 1.0, t, 0.0, t)

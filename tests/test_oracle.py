@@ -402,3 +402,23 @@ def test_public_headers_are_plain_c():
         subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + inc, p], check=True)
         if shutil.which("g++"):
             subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, "-x", "c++", p], check=True)
+
+
+def test_reference_bsplineop_family_agrees_with_the_dense_operators():
+    """oracle/ref_shim/ref_glue.c restates the four suzerain_bsplineop_{accumulate,apply}{,_complex} drivers
+    (suzerain/bsplineop.c:222-381) around the reference's own dgbmv / zgbmv_d_z: all of them against the dense
+    collocation operators, incl. the in-place forms and beta != 0."""
+    case = pc.make_case("tiny_16x24x16", max_pencils=4, k=6, Ny=41)
+    P = pc.oracle_problem(case, "ref")
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((7, 41)); y = rng.standard_normal((7, 41))
+    xc = x + 1j * rng.standard_normal((7, 41)); yc = y - 2j * x
+    for d in range(3):
+        D = case.bop.dense(d)
+        scale = np.abs(D).sum(axis=1).max()
+        assert np.abs(P.bsplineop_accumulate(d, 1.3, x, -0.6, y) - (1.3 * x @ D.T - 0.6 * y)).max() <= 1e-14 * scale * 10
+        assert np.abs(P.bsplineop_accumulate(d, 1.3, x) - 1.3 * x @ D.T).max() <= 1e-14 * scale * 10
+        assert np.abs(P.bsplineop_apply(d, 2.0, x) - 2.0 * x @ D.T).max() <= 1e-14 * scale * 10
+        assert np.abs(P.bsplineop_apply(d, 2.0, xc) - 2.0 * xc @ D.T).max() <= 1e-14 * scale * 10
+        want = (1.3 + 0.4j) * xc @ D.T + (0.7 - 0.2j) * yc
+        assert np.abs(P.bsplineop_accumulate_complex(d, 1.3 + 0.4j, xc, 0.7 - 0.2j, yc) - want).max() <= 1e-14 * scale * 10
