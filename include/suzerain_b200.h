@@ -189,6 +189,20 @@ int  szb_imexop_set_refs(szb_imexop *op, const szb_rholut_imexop_ref *r,
 #define SZB_REFERENCES_ROWS  42
 #define SZB_REFERENCES_FIRST 5
 int  szb_imexop_set_refs_device(szb_imexop *op, const double *d_references, int ld, void *stream);
+/* The producer of that block: collect_references (apps/perfect/perfect.cpp:1266-1400).  Sums the 42 quantities
+ * of apps/perfect/references.hpp:83-128 over the (z, x) points of the `ny` local wall-normal planes [y0, y0 + ny)
+ * of the physical-space state d_sphys (fields e, mx, my, mz, rho in ndx order, each [ny][nzx] doubles, field
+ * stride `field_stride` doubles: the physical_view of suzerain/physical_view.hpp:44-87), multiplies by `scale`
+ * and writes d_refs (42 x Ny, column-major, ld = 42); the columns of planes this rank does not own are zeroed
+ * (:1275-1277), so that an all-reduce(SUM) over ranks completes the profile.  Single rank: scale = chi =
+ * 1 / (dNx dNz) (suzerain/pencil_grid.hpp:159-163); several ranks: scale = 1, all-reduce, then scale by chi
+ * (:1396-1399).  top_is_inviscid: mu = lambda = 0 on the global plane Ny - 1 (one-sided grids, :1287-1290).
+ * beta is the viscosity exponent of definition_scenario; Re and Pr of `scenario` are not used.
+ * d_workspace: `*workspace_needed` bytes of device scratch (query with d_sphys = d_refs = NULL).
+ * Deterministic (no atomics); asynchronous on `stream`. */
+int  szb_collect_references_device(const szb_rholut_imexop_scenario *scenario, double beta, int Ny, int y0, int ny,
+        size_t nzx, const double *d_sphys, size_t field_stride, int top_is_inviscid, double scale,
+        double *d_refs, void *d_workspace, size_t workspace_bytes, size_t *workspace_needed, void *stream);
 int  szb_imexop_set_isothermal(szb_imexop *op, const szb_isothermal *iso);
 /* 5x5 column-major Giles matrices (upper_nrbc_{a,b,c},
  * operator_hybrid_isothermal.cpp:771-777); any may be NULL. */

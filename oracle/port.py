@@ -412,3 +412,76 @@ def zcgbsvx(trans, ab, afb, n, kl, ku, ipiv, b, aiter=1, dmax=5, tolsc=0.0):
     if np.isnan(res):
         x[:] = np.nan
     return x, diter
+
+
+# ---------------------------------------------------------------------------
+# Reference profiles from the physical-space state: collect_references
+# (apps/perfect/perfect.cpp:1266-1400) with the equation-of-state helpers of suzerain/rholut.hpp.
+# Pinned against the known answers of the reference's tests/test_rholut.cpp
+# (tests/golden/rholut_known_answers.json, tests/test_oracle.py).
+# ---------------------------------------------------------------------------
+REFERENCE_QUANTITIES = (                      # apps/perfect/references.hpp:83-128, in row order
+    "rho p p2 T a u v w u2 uu uv uw vv vw ww nu nu_u nu_v nu_w nu_u2 nu_uu nu_uv nu_uw nu_vv nu_vw nu_ww "
+    "ex_gradrho ey_gradrho ez_gradrho e_divm e_deltarho rhou rhov rhow rhoE rhouu rhouv rhouw rhovv rhovw rhoww "
+    "rhoEE").split()
+
+
+def p_T_mu_lambda(alpha, beta, gamma, Ma, rho, m, e):
+    """suzerain/rholut.hpp:769-790 (m: (3, ...) array)."""
+    rho_inverse = 1 / rho
+    m2 = m[0] * m[0] + m[1] * m[1] + m[2] * m[2]
+    p = (gamma - 1) * (e - Ma * Ma * rho_inverse * m2 / 2)
+    T = gamma * p * rho_inverse
+    mu = np.power(T, beta)
+    lam = (alpha - 2.0 / 3.0) * mu
+    return p, T, mu, lam
+
+
+def explicit_div_e_plus_p_u_refcoeff_div_m(rho, e, p):
+    return (e + p) / rho                                          # suzerain/rholt.hpp:675-681
+
+
+def explicit_div_e_plus_p_u_refcoeff_grad_rho(gamma, rho, m, e, p):
+    return (((gamma - 2) * e - 2 * p) / (rho * rho)) * m          # suzerain/rholt.hpp:701-709
+
+
+def explicit_mu_div_grad_T_refcoeff_div_grad_rho(gamma, mu, rho, e, p):
+    return mu / (rho * rho) * ((gamma - 1) * e - 2 * p)           # suzerain/rholt.hpp:1481-1489
+
+
+def collect_references(alpha, beta, gamma, Ma, sphys, top_is_inviscid=False, with_abs=False):
+    """Sums over (z, x) of the 42 reference quantities at every y: the loop body of collect_references
+    (apps/perfect/perfect.cpp:1279-1393) before MPI_Allreduce and the chi scaling.  sphys: (5, Ny, Nz, Nx) real,
+    fields in ndx order e, mx, my, mz, rho.  top_is_inviscid: mu = lambda = 0 on the last plane (one-sided grids,
+    :1287-1290, 1311-1316).  Returns (42, Ny) [and the sums of absolute values, for error scaling]."""
+    sphys = np.asarray(sphys, dtype=np.float64)
+    e, mx, my, mz, rho = (sphys[i] for i in range(5))
+    m = np.stack([mx, my, mz])
+    p, T, mu, lam = p_T_mu_lambda(alpha, beta, gamma, Ma, rho, m, e)
+    if top_is_inviscid:
+        mu = mu.copy(); mu[-1] = 0.0
+    u = m / rho
+    ux, uy, uz = u
+    u2 = ux * ux + uy * uy + uz * uz
+    nu = mu / rho
+    eg = explicit_div_e_plus_p_u_refcoeff_grad_rho(gamma, rho, m, e, p)
+    q = {
+        "rho": rho, "p": p, "p2": p * p, "T": T, "a": np.sqrt(T), "u": ux, "v": uy, "w": uz, "u2": u2,
+        "uu": ux * ux, "uv": ux * uy, "uw": ux * uz, "vv": uy * uy, "vw": uy * uz, "ww": uz * uz,
+        "nu": nu, "nu_u": nu * ux, "nu_v": nu * uy, "nu_w": nu * uz, "nu_u2": nu * u2,
+        "nu_uu": nu * ux * ux, "nu_uv": nu * ux * uy, "nu_uw": nu * ux * uz, "nu_vv": nu * uy * uy,
+        "nu_vw": nu * uy * uz, "nu_ww": nu * uz * uz,
+        "ex_gradrho": eg[0], "ey_gradrho": eg[1], "ez_gradrho": eg[2],
+        "e_divm": explicit_div_e_plus_p_u_refcoeff_div_m(rho, e, p),
+        "e_deltarho": explicit_mu_div_grad_T_refcoeff_div_grad_rho(gamma, mu, rho, e, p),
+        "rhou": mx, "rhov": my, "rhow": mz, "rhoE": e,
+        "rhouu": mx * mx / rho, "rhouv": mx * my / rho, "rhouw": mx * mz / rho, "rhovv": my * my / rho,
+        "rhovw": my * mz / rho, "rhoww": mz * mz / rho, "rhoEE": e * e / rho,
+    }
+    # the reference sums with Kahan compensation (apps/perfect/perfect.hpp:78-86): extended precision here
+    ld = np.longdouble
+    out = np.stack([np.asarray(q[k], dtype=ld).sum(axis=(1, 2)).astype(np.float64) for k in REFERENCE_QUANTITIES])
+    if not with_abs:
+        return out
+    mag = np.stack([np.abs(q[k]).sum(axis=(1, 2)) for k in REFERENCE_QUANTITIES])
+    return out, mag

@@ -9,10 +9,10 @@ from . import lowstorage  # noqa: F401
 from .pencil import PencilGrid  # noqa: F401
 from .api import (BsplineOp, ImexOp, OperatorHybridIsothermal, OperatorHybridIsothermalDevice, SolverSpec,  # noqa: F401
                   bsplineop_accumulate_batch, bsplineop_accumulate_complex_batch, bsplineop_apply_batch,
-                  diffwave_accumulate, diffwave_apply,
+                  collect_references, diffwave_accumulate, diffwave_apply,
                   htstretch_breakpoints, wavegrid, wavenumbers)
 
 __all__ = ["lib", "lowstorage", "PencilGrid", "BsplineOp", "ImexOp", "OperatorHybridIsothermal", "OperatorHybridIsothermalDevice", "SolverSpec",
            "bsplineop_accumulate_batch", "bsplineop_accumulate_complex_batch", "bsplineop_apply_batch",
-           "diffwave_accumulate", "diffwave_apply",
+           "collect_references", "diffwave_accumulate", "diffwave_apply",
            "htstretch_breakpoints", "wavegrid", "wavenumbers"]

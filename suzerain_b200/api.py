@@ -344,6 +344,45 @@ def wavenumbers(g):
     return km, kn, act.astype(bool)
 
 
+def collect_references(scenario, beta, sphys, Ny=None, y0=0, chi=None, top_is_inviscid=False, group=None,
+                       out=None, stream=None):
+    """Reference profiles from the physical-space state: collect_references (apps/perfect/perfect.cpp:1266-1400).
+    sphys: device tensor (5, ny, nz, nx) float64, fields e, mx, my, mz, rho on this rank's planes [y0, y0 + ny) of
+    Ny; scenario: dict with Ma, alpha, gamma (Re, Pr unused); beta: viscosity exponent; chi = 1 / (dNx dNz), default
+    from the local (nz, nx) (right for a single rank or a y-decomposition).  With torch.distributed initialised (or
+    `group` given) the sums are all-reduced over ranks before the scaling, as the reference's MPI_Allreduce.
+    Returns the (Ny, 42) device tensor whose memory is the reference's 42 x Ny column-major block: feed it to
+    ImexOp.set_refs_device."""
+    import torch
+    import torch.distributed as dist
+    assert sphys.is_cuda and sphys.dtype == torch.float64 and sphys.dim() == 4 and sphys.shape[0] == 5
+    assert sphys[0].is_contiguous()
+    ny, nz, nx = (int(v) for v in sphys.shape[1:])
+    Ny = ny if Ny is None else int(Ny)
+    chi = 1.0 / (nz * nx) if chi is None else float(chi)
+    multi = group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+    s = _L.Scenario(float(scenario.get("Re", 0.0)), float(scenario.get("Pr", 0.0)), float(scenario["Ma"]),
+                    float(scenario["alpha"]), float(scenario["gamma"]))
+    st = stream or torch.cuda.current_stream(sphys.device)
+    L = _L.load()
+    need = C.c_size_t(0)
+    _L.check("szb_collect_references_device",
+             L.szb_collect_references_device(C.byref(s), float(beta), Ny, int(y0), ny, nz * nx, None, 0, 0, 1.0, None, None,
+                                             0, C.byref(need), None))
+    work = torch.empty(max(need.value, 8) // 8, dtype=torch.float64, device=sphys.device)
+    refs = out if out is not None else torch.empty((Ny, 42), dtype=torch.float64, device=sphys.device)
+    assert refs.is_contiguous() and refs.shape == (Ny, 42)
+    rc = L.szb_collect_references_device(C.byref(s), float(beta), Ny, int(y0), ny, nz * nx, C.c_void_p(sphys.data_ptr()),
+                                         sphys.stride(0), int(bool(top_is_inviscid)), 1.0 if multi else chi,
+                                         C.c_void_p(refs.data_ptr()), C.c_void_p(work.data_ptr()), work.numel() * 8,
+                                         C.byref(need), C.c_void_p(st.cuda_stream))
+    _L.check("szb_collect_references_device", rc)
+    if multi:
+        dist.all_reduce(refs, op=dist.ReduceOp.SUM, group=group)
+        refs.mul_(chi)
+    return refs
+
+
 def bsplineop_accumulate_complex_batch(bop, d, alpha, x, beta, y, stream=None):
     """y <- alpha D^(d) x + beta y over the rows of the device tensors x, y (nrhs, n) complex128:
     suzerain_bsplineop_accumulate_complex as batched by operator_tools.hpp:77-116."""

@@ -94,6 +94,9 @@ PROTOTYPES = {
     "szb_bsplineop_accumulate_batch": (C.c_int, [c_void_p, C.c_int, C.c_int, C.c_double, c_void_p, C.c_size_t,
                                                  C.c_double, c_void_p, C.c_size_t, c_void_p]),
     "szb_bsplineop_apply_batch": (C.c_int, [c_void_p, C.c_int, C.c_int, C.c_double, c_void_p, C.c_size_t, c_void_p]),
+    "szb_collect_references_device": (C.c_int, [c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_size_t, c_void_p,
+                                                C.c_size_t, C.c_int, C.c_double, c_void_p, c_void_p, C.c_size_t,
+                                                C.POINTER(C.c_size_t), c_void_p]),
     "szb_diffwave_apply_batch": (C.c_int, [C.c_int, C.c_int, D2, c_void_p, c_void_p, C.c_int, c_void_p]),
     "szb_diffwave_accumulate_batch": (C.c_int, [C.c_int, C.c_int, D2, c_void_p, D2, c_void_p, c_void_p,
                                                 C.c_int, c_void_p]),

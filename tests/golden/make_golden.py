@@ -11,6 +11,8 @@ the fixtures are committed, the reference sources are not copied).
                         operators D_T[d] for k = 2, 3, 4 (and the k=4
                         single-interval "almost dense" case)
   lapack_gbtrf.json     tests/test_lapack.c:35-76       4x4 dgbtrf + dgbcon case
+  rholut_known_answers.json tests/test_rholut.cpp:37-108, 155-240  the test field (rho, m, e at (1,2,3)) and the
+                        200-bit Sage values of p, T, mu, lambda for alpha=5, beta=2/3, gamma=1.4, Ma=3.5
 
 Usage: python tests/golden/make_golden.py [/root/reference]
 """
@@ -117,7 +119,30 @@ def bsplineop():
     return cases
 
 
+def rholut():
+    """tests/test_rholut.cpp: the test field of rholut_test_data() and the known answers of the
+    rholut_p_T_mu_lambda case (long-double literals from test_rholut.sage)."""
+    raw = strip_comments(open(os.path.join(REF, "tests/test_rholut.cpp")).read())
+    num = r"(-?\s*[\d.]+(?:[eE][-+]?\d+)?)L?"
+    data = raw[raw.index("void rholut_test_data("):]
+    data = data[:data.index("BOOST_AUTO_TEST_CASE")]
+    val = lambda name: float(re.search(re.escape(name) + r"\s*=\s*" + num + r"\s*;", data).group(1).replace(" ", ""))
+    case = raw[raw.index("BOOST_AUTO_TEST_CASE( rholut_p_T_mu_lambda )"):]
+    case = case[:case.index("BOOST_AUTO_TEST_CASE", 10)]
+    par = lambda name: float(eval(re.search(r"const double " + name + r"\s*=\s*([^;]+);", case).group(1),
+                                  {"__builtins__": {}}))
+    ans = lambda name: float(re.search(r"BOOST_CHECK_CLOSE\(" + name + r",\s*" + num, case).group(1))
+    out = {"source": "tests/test_rholut.cpp:37-108 (rholut_test_data), :155-240 (rholut_p_T_mu_lambda)",
+           "tolerance": "1e3 * eps relative (BOOST_CHECK_CLOSE is in percent: 1e3 eps percent = 1e1 eps)",
+           "rho": val("rho"), "m": [val("m(0)"), val("m(1)"), val("m(2)")], "e": val("e"),
+           "alpha": par("alpha"), "beta": par("beta"), "gamma": par("gamma"), "Ma": par("Ma"),
+           "p": ans("p"), "T": ans("T"), "mu": ans("mu"), "lambda": ans("lambda")}
+    json.dump(out, open(os.path.join(OUT, "rholut_known_answers.json"), "w"), indent=1)
+    return out
+
+
 if __name__ == "__main__":
     bsmbsm()
+    print("rholut:", rholut())
     cs = bsplineop()
     print("bsplineop cases:", [(c["name"], c["k"], [(d["d"], d["kl"], d["ku"]) for d in c["D_T"]]) for c in cs])

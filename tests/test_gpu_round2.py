@@ -510,3 +510,97 @@ def test_bsplineop_real_and_in_place_match_reference(dev, k, Ny, nrhs):
     t = torch.from_numpy(xr.copy()).to(dev)
     with pytest.raises(Exception):
         sz.bsplineop_accumulate_batch(case.bop, 0, 1.0, t, 0.0, t)
+
+
+# ---------------------------------------------------------------------------
+# collect_references: the physical-space sweep that produces the operator's reference profiles
+# (apps/perfect/perfect.cpp:1266-1400)
+# ---------------------------------------------------------------------------
+def _physical_state(Ny, Nz, Nx, gamma, Ma, seed=21):
+    rng = np.random.default_rng(seed)
+    y = np.linspace(-1, 1, Ny)[:, None, None]
+    rho = 1.0 + 0.2 * rng.uniform(-1, 1, (Ny, Nz, Nx)) + 0.1 * y
+    u = 0.6 * (1 - y * y) + 0.2 * rng.standard_normal((Ny, Nz, Nx))
+    v = 0.1 * rng.standard_normal((Ny, Nz, Nx))
+    w = 0.15 * rng.standard_normal((Ny, Nz, Nx))
+    T = 1.0 + 0.3 * rng.uniform(-1, 1, (Ny, Nz, Nx)) + 0.2 * y * y
+    p = rho * T / gamma
+    e = p / (gamma - 1) + Ma * Ma * rho * (u * u + v * v + w * w) / 2
+    return np.stack([e, rho * u, rho * v, rho * w, rho])
+
+
+@pytest.mark.parametrize("shape,top", [((24, 12, 18), False), ((24, 12, 18), True), ((17, 5, 7), True),
+                                       ((96, 96, 144), False)])
+def test_collect_references_matches_oracle(dev, shape, top):
+    import torch
+    import suzerain_b200 as sz
+    from oracle import port
+    scen = dict(Re=3000.0, Pr=0.7, Ma=1.5, alpha=0.0, gamma=1.4)
+    beta = 2.0 / 3.0
+    Ny, Nz, Nx = shape
+    s = _physical_state(Ny, Nz, Nx, scen["gamma"], scen["Ma"])
+    want, mag = port.collect_references(scen["alpha"], beta, scen["gamma"], scen["Ma"], s, top, with_abs=True)
+    chi = 1.0 / (Nz * Nx)
+    d = torch.from_numpy(s).to(dev)
+    got = sz.collect_references(scen, beta, d, top_is_inviscid=top)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy().T                                           # (42, Ny)
+    # tolerance relative to the sum of magnitudes of each (quantity, plane): the sums themselves may cancel
+    err = np.abs(got - want * chi) / np.maximum(mag * chi, 1e-300)
+    assert err.max() <= TOL, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    if top:
+        nu_row = port.REFERENCE_QUANTITIES.index("nu")
+        assert np.all(got[nu_row:nu_row + 11, -1] == 0.0) and got[port.REFERENCE_QUANTITIES.index("e_deltarho"), -1] == 0.0
+    # same bits on a second run (no atomics)
+    again = sz.collect_references(scen, beta, d, top_is_inviscid=top).cpu().numpy().T
+    assert np.array_equal(again, got)
+    # a rank that owns planes [y0, y0 + ny) only: its columns, zeros elsewhere; the pieces add up
+    y0, ny = Ny // 3, Ny // 2
+    part = sz.collect_references(scen, beta, d[:, y0:y0 + ny].contiguous(), Ny=Ny, y0=y0,
+                                 top_is_inviscid=top).cpu().numpy().T
+    # (another launch shape, hence another summation tree: equal to rounding, not to the bit)
+    assert np.abs(part[:, y0:y0 + ny] - got[:, y0:y0 + ny]).max() <= TOL * np.abs(mag * chi).max()
+    assert np.all(part[:, :y0] == 0.0) and np.all(part[:, y0 + ny:] == 0.0)
+
+
+def test_collect_references_feeds_the_operator(dev):
+    """physical state -> collect_references -> set_refs_device -> accumulate equals the host path that sets the 26
+    profiles from the oracle's means; and at the full physical extent of the bench grid the linear rows are plain
+    sums (size-independent property)."""
+    import torch
+    import suzerain_b200 as sz
+    from oracle import port
+    case = pc.make_case("tiny_16x24x16", max_pencils=8)
+    Ny = case.bop.n
+    scen = dict(case.scenario)
+    beta = 2.0 / 3.0
+    s = _physical_state(Ny, 12, 18, scen["gamma"], scen["Ma"], seed=4)
+    d = torch.from_numpy(s).to(dev)
+    refs42 = sz.collect_references(scen, beta, d)
+    want = port.collect_references(scen["alpha"], beta, scen["gamma"], scen["Ma"], s) / (12 * 18)
+    first = port.REFERENCE_QUANTITIES.index("u")
+    x = torch.from_numpy(case.x).to(dev)
+    km, kn = torch.from_numpy(case.km).to(dev), torch.from_numpy(case.kn).to(dev)
+    outs = []
+    for use_device in (True, False):
+        op = pc.make_imexop(case)
+        if use_device:
+            op.set_refs_device(refs42)
+        else:
+            op.set_refs(np.ascontiguousarray(want[first:first + 26]))
+        y = torch.zeros_like(x)
+        op.accumulate_batch(case.phi, km, kn, x, 0.0, y)
+        torch.cuda.synchronize()
+        outs.append(y.cpu().numpy())
+    assert pc.relmax(outs[0], outs[1]) <= TOL
+    # full size: 96 x 288 x 288 (the dealiased physical extent of channel_192x96x192)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    big = torch.rand((5, 96, 288, 288), dtype=torch.float64, device=dev, generator=g) + 1.0
+    big[0] += 20.0                                                      # e large enough for p > 0 at Ma = 1.5, |m| <= 2 sqrt 3
+    r = sz.collect_references(scen, beta, big)
+    torch.cuda.synchronize()
+    for name, f in (("rhoE", 0), ("rhou", 1), ("rhov", 2), ("rhow", 3), ("rho", 4)):
+        mean = big[f].sum(dim=(1, 2)) / (288 * 288)
+        col = r[:, port.REFERENCE_QUANTITIES.index(name)]
+        assert float(((col - mean).abs() / mean.abs()).max()) <= TOL
+    assert bool(torch.isfinite(r).all())

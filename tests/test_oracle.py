@@ -422,3 +422,61 @@ def test_reference_bsplineop_family_agrees_with_the_dense_operators():
         assert np.abs(P.bsplineop_apply(d, 2.0, xc) - 2.0 * xc @ D.T).max() <= 1e-14 * scale * 10
         want = (1.3 + 0.4j) * xc @ D.T + (0.7 - 0.2j) * yc
         assert np.abs(P.bsplineop_accumulate_complex(d, 1.3 + 0.4j, xc, 0.7 - 0.2j, yc) - want).max() <= 1e-14 * scale * 10
+
+
+def test_equation_of_state_port_matches_the_reference_known_answers():
+    """oracle.port.p_T_mu_lambda against the 200-bit Sage values of tests/test_rholut.cpp:155-240 (fixture:
+    tests/golden/rholut_known_answers.json), and the three reference coefficients of collect_references against
+    the closed forms the reference's own tests check them with (tests/test_rholut.cpp:395-420, 845-860)."""
+    g = json.load(open(os.path.join(pc.ROOT, "tests", "golden", "rholut_known_answers.json")))
+    p, T, mu, lam = port.p_T_mu_lambda(g["alpha"], g["beta"], g["gamma"], g["Ma"], g["rho"], np.array(g["m"]), g["e"])
+    eps = np.finfo(float).eps
+    for got, key in ((p, "p"), (T, "T"), (mu, "mu"), (lam, "lambda")):
+        assert abs(got / g[key] - 1) <= 10 * eps                     # BOOST_CHECK_CLOSE(.., eps * 1e3) is in percent
+    gamma, Ma, mu, rho, pp = 1.4, 3.5, 4181.0, 67.0, 55.0
+    m = np.array([144.0, 233.0, 377.0])
+    e = pp / (gamma - 1) + Ma * Ma * (m @ m) / (2 * rho)
+    assert abs(port.explicit_mu_div_grad_T_refcoeff_div_grad_rho(gamma, mu, rho, e, pp)
+               / (mu / rho / rho * ((gamma - 1) * e - 2 * pp)) - 1) <= 10 * eps
+    assert abs(port.explicit_div_e_plus_p_u_refcoeff_div_m(rho, e, pp) / ((e + pp) / rho) - 1) <= 10 * eps
+    assert np.allclose(port.explicit_div_e_plus_p_u_refcoeff_grad_rho(gamma, rho, m, e, pp),
+                       m * ((gamma - 2) * e - 2 * pp) / rho ** 2, rtol=10 * eps, atol=0)
+
+
+def test_collect_references_port_against_a_point_by_point_loop():
+    """The vectorised oracle against the reference's loop written out point by point with Kahan sums
+    (apps/perfect/perfect.cpp:1279-1393, perfect.hpp:78-86), incl. the inviscid top plane of one-sided grids."""
+    import math
+    rng = np.random.default_rng(8)
+    Ny, Nz, Nx = 4, 3, 5
+    gamma, Ma, alpha, beta = 1.4, 1.5, 0.0, 2.0 / 3.0
+    rho = 1 + 0.2 * rng.uniform(-1, 1, (Ny, Nz, Nx)); u = 0.3 * rng.standard_normal((3, Ny, Nz, Nx))
+    T = 1 + 0.2 * rng.uniform(-1, 1, (Ny, Nz, Nx))
+    p = rho * T / gamma
+    e = p / (gamma - 1) + Ma * Ma * rho * (u ** 2).sum(axis=0) / 2
+    s = np.stack([e, rho * u[0], rho * u[1], rho * u[2], rho])
+    for top in (False, True):
+        got = port.collect_references(alpha, beta, gamma, Ma, s, top)
+        want = np.zeros((42, Ny))
+        for j in range(Ny):
+            rows = [[] for _ in range(42)]
+            for k in range(Nz):
+                for i in range(Nx):
+                    ee, mx, my, mz, r = s[:, j, k, i]
+                    pr = (gamma - 1) * (ee - Ma * Ma / r * (mx * mx + my * my + mz * mz) / 2)
+                    TT = gamma * pr / r
+                    mu = TT ** beta * (0 if (top and j == Ny - 1) else 1)
+                    ux, uy, uz = mx / r, my / r, mz / r
+                    u2 = ux * ux + uy * uy + uz * uz
+                    nu = mu / r
+                    cg = ((gamma - 2) * ee - 2 * pr) / (r * r)
+                    vals = [r, pr, pr * pr, TT, math.sqrt(TT), ux, uy, uz, u2, ux * ux, ux * uy, ux * uz, uy * uy, uy * uz,
+                            uz * uz, nu, nu * ux, nu * uy, nu * uz, nu * u2, nu * ux * ux, nu * ux * uy, nu * ux * uz,
+                            nu * uy * uy, nu * uy * uz, nu * uz * uz, cg * mx, cg * my, cg * mz, (ee + pr) / r,
+                            mu / (r * r) * ((gamma - 1) * ee - 2 * pr), mx, my, mz, ee, mx * mx / r, mx * my / r,
+                            mx * mz / r, my * my / r, my * mz / r, mz * mz / r, ee * ee / r]
+                    for q, v in enumerate(vals):
+                        rows[q].append(v)
+            want[:, j] = [math.fsum(r_) for r_ in rows]
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+        assert len(port.REFERENCE_QUANTITIES) == 42 and port.REFERENCE_QUANTITIES[5:31][0] == "u"

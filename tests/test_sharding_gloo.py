@@ -100,3 +100,54 @@ def test_cost_weighted_shards_cover_the_grid_and_balance_the_weights():
             m = shard.shard_wavegrid(g, r, world)
             sums0.append(w[m.dkbz - g.dkbz:m.dkez - g.dkbz].sum())
         assert max(sums) <= max(sums0) + 1e-9
+
+
+def _refs_worker(rank, world, port_no, q):
+    """collect_references over ranks: every rank sums its own planes / z-rows into a zeroed 42 x Ny block,
+    all-reduce(SUM), then the chi scaling (apps/perfect/perfect.cpp:1275-1277, 1396-1399).  The oracle stands
+    in for the device kernel; the subject is the protocol suzerain_b200.api.collect_references follows."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from oracle import port
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Ny, Nz, Nx = 12, 6, 8
+        gamma, Ma, alpha, beta = 1.4, 1.5, 0.0, 2.0 / 3.0
+        rng = np.random.default_rng(2)
+        rho = 1 + 0.2 * rng.uniform(-1, 1, (Ny, Nz, Nx)); u = 0.3 * rng.standard_normal((3, Ny, Nz, Nx))
+        p = rho * (1 + 0.2 * rng.uniform(-1, 1, (Ny, Nz, Nx))) / gamma
+        s = np.stack([p / (gamma - 1) + Ma * Ma * rho * (u ** 2).sum(axis=0) / 2, rho * u[0], rho * u[1], rho * u[2], rho])
+        # rank 0: planes 0..6 (all z); rank 1: planes 7..11 -- and, to exercise partial planes, rank 1 also
+        # owns the upper z half of plane 6 while rank 0 only has its lower half
+        block = np.zeros((Ny, 42))
+        if rank == 0:
+            block[:6] = port.collect_references(alpha, beta, gamma, Ma, s[:, :6], False).T
+            block[6:7] = port.collect_references(alpha, beta, gamma, Ma, s[:, 6:7, :3], False).T
+        else:
+            block[7:] = port.collect_references(alpha, beta, gamma, Ma, s[:, 7:], True).T      # owns the top plane
+            block[6:7] = port.collect_references(alpha, beta, gamma, Ma, s[:, 6:7, 3:], False).T
+        t = torch.from_numpy(block)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.mul_(1.0 / (Nz * Nx))
+        if rank == 0:
+            want = port.collect_references(alpha, beta, gamma, Ma, s, True).T / (Nz * Nx)
+            q.put(float(np.abs(t.numpy() - want).max() / np.abs(want).max()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_reference_collection_matches_single_rank():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_refs_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) <= 1e-14

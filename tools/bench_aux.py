@@ -51,6 +51,24 @@ ms = timed(lambda: [sz.diffwave_apply(1, 1, 1.0, a, g) for a in xs])
 out["kernels"]["diffwave_apply"] = {"ms": ms, "GB/s": 2 * nbytes / ms / 1e6, "frac": 2 * nbytes / ms / 1e6 / peak,
                                     "note": "upper bound on bytes: dealiased pencils are written, not read"}
 
+# the other members of the bsplineop family: in place (one read, one write) and real pencils
+ms = timed(lambda: sz.bsplineop_apply_batch(wl.bop, 0, 1.0, X2))
+out["kernels"]["bop_apply_in_place(complex)"] = {"ms": ms, "GB/s": 2 * nbytes / ms / 1e6, "frac": 2 * nbytes / ms / 1e6 / peak}
+XR, YR = torch.view_as_real(x).reshape(-1, Ny), torch.view_as_real(y).reshape(-1, Ny)
+ms = timed(lambda: sz.bsplineop_accumulate_batch(wl.bop, 1, 1.0, XR, 0.5, YR))
+out["kernels"]["bop_accumulate(real, beta!=0)"] = {"ms": ms, "GB/s": 3 * nbytes / ms / 1e6, "frac": 3 * nbytes / ms / 1e6 / peak}
+# collect_references on the dealiased physical extent of the grid: five fields in, 42 x Ny out
+pz, px = g.dNz, g.dNx
+gen = torch.Generator(device=dev); gen.manual_seed(1)
+sphys = torch.rand((5, Ny, pz, px), dtype=torch.float64, device=dev, generator=gen) + 1.0
+sphys[0] += 5.0
+scen = dict(Re=3000.0, Pr=0.7, Ma=1.5, alpha=0.0, gamma=1.4)
+refs42 = torch.empty((Ny, 42), dtype=torch.float64, device=dev)
+ms = timed(lambda: sz.collect_references(scen, 2.0 / 3.0, sphys, out=refs42))
+pb = sphys.numel() * 8
+out["kernels"]["collect_references"] = {"ms": ms, "GB/s": pb / ms / 1e6, "frac": pb / ms / 1e6 / peak,
+                                        "points": int(Ny * pz * px), "note": "algorithmic bytes = the five physical fields"}
+
 # invert under the other linearisation / solver specifications, all active pencils
 act = np.flatnonzero(wl.act)
 km = torch.from_numpy(wl.km[act]).to(dev); kn = torch.from_numpy(wl.kn[act]).to(dev)
