@@ -316,11 +316,7 @@ invert_pipe_kernel(const PipeArgs A)
     constexpr int KL = W::KL, KU = W::KU, RW = W::RW, NS = W::NS, CW = W::CW, NT = W::NT, NTU = W::NTU;
     constexpr int BAR_ALL = 1, BAR_UPD = 6, BAR_PP = 7;
     constexpr int BAR_C3 = 8;           // SZB_PIPE_SPLITU0: panel warps arrive once columns 0..3 are published
-#if defined(SZB_PIPE_SPLITU0) && SZB_PIPE_SPLITU0 == 2
-    constexpr int C3N = NTU + W::NTA + 32 * W::NWP;
-#else
     constexpr int C3N = NTU + 32 * W::NWP;
-#endif
     (void) BAR_C3; (void) C3N;
     const size_t lstride = ((size_t) N * KL + 7) & ~(size_t) 7;     // per buffer, whole 128-byte lines
     cplx *lwork = A.lwork + (size_t) blockIdx.x * 2 * lstride;
@@ -658,14 +654,8 @@ invert_pipe_kernel(const PipeArgs A)
                 // ---- U0a(t): block t+1 against pivots 0..3 of THIS panel, as soon as the panel warps have
                 // published them (they are in their last column step meanwhile).  Every thread redoes the
                 // small unit-lower-triangular fix-up of the four pivot rows for its column. ----
-#if SZB_PIPE_SPLITU0 == 2
-                // variant 2 (UNTESTED, for round 2): the assembly warps, which idle after A(t), take the early
-                // update; the update warps only announce that R(t-1) is done
-                bar_arrive_n<BAR_C3>(C3N);
-#else
                 bar_sync_n<BAR_C3>(C3N);
                 early_block_update<W>(S, sbase, jc, par, tid, NTU);
-#endif
 #endif
                 bar_sync_n<BAR_ALL>(NT);
                 PROF_MARK(5);
@@ -692,10 +682,6 @@ invert_pipe_kernel(const PipeArgs A)
                     assemble_block<W>(K, S, DStaged(K, S.drow + par * 3 * W::LDMAX, yI), km, kn, yI, dst, ta, W::NTA);
 #endif
                 stage_rowblock<W>(K, S, yI + 1, par ^ 1, ta, W::NTA);
-#if defined(SZB_PIPE_SPLITU0) && SZB_PIPE_SPLITU0 == 2
-                bar_sync_n<BAR_C3>(C3N);
-                early_block_update<W>(S, sbase, jc, par, ta, W::NTA);
-#endif
                 bar_sync_n<BAR_ALL>(NT);
                 info = S.misc[4 + buf];
                 if (info) break;

@@ -349,7 +349,7 @@ __device__ __forceinline__ void urows_column(const SM &S, int jr, int cs, cplx *
 
 // ---------------------------------------------------------------------------------------------
 // U(t): rank-5 update of trailing columns i = i0, i0 + istep, ... < ilim (column j + 5 + i of the matrix), NCHX of them
-// at once, lane = row.  Column indices past the last one are pointed at the retired column slot jc: dead data.
+// at once, lane = row.  Column indices past the last one are pointed at the retired column slot jc (read, not stored).
 // Explicit shared-memory addresses and loads in program order: every pivot-row operand is re-loaded right after
 // its use, four complex updates ahead of the next one (the compiler's own schedule went column by column, a chain
 // of ten dependent FMAs behind each load).
@@ -367,11 +367,13 @@ __device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, i
     constexpr unsigned ROWB = CW * sizeof(cplx);
     for (int m0 = 0; i0 + istep * m0 < ilim; m0 += NCHX) {
         unsigned ca[NCHX];
+        bool cv[NCHX];                                          // a real column: the dummy one is read, never written
 #pragma unroll
         for (int x = 0; x < NCHX; ++x) {
             const int i = i0 + istep * (m0 + x);
             int c = jc + P + i; if (c >= CW) c -= CW;
-            ca[x] = prow_sa + 16u * (unsigned) (i < ilim ? c : jc);
+            cv[x] = i < ilim;
+            ca[x] = prow_sa + 16u * (unsigned) (cv[x] ? c : jc);
         }
         if (lane < W::NMAIN) {
             cplx w[NCHX], u[NCHX];
@@ -392,7 +394,7 @@ __device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, i
                 lk = ln;
             }
 #pragma unroll
-            for (int x = 0; x < NCHX; ++x) sts_if(ca[x] + dro, w[x], true);
+            for (int x = 0; x < NCHX; ++x) sts_if(ca[x] + dro, w[x], cv[x]);
         }
         // tail rows (positions 5 + NMAIN .. RW): one element per lane
         for (int e = lane; e < W::NTAIL * NCHX; e += 32) {
@@ -410,7 +412,7 @@ __device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, i
             for (int k = 0; k < P; ++k) { uu[k] = lds_c(pu + k * ROWB); ll[k] = lds_c(pl + 16 * k); }
 #pragma unroll
             for (int k = 0; k < P; ++k) submul(w, ll[k], uu[k]);
-            sts_if(pw, w, true);
+            sts_if(pw, w, i < ilim);
         }
     }
 }

@@ -89,10 +89,18 @@ collect_references_kernel(const CollectArgs A)
         const double2 *y2 = reinterpret_cast<const double2 *>(A.my + base + lo);
         const double2 *z2 = reinterpret_cast<const double2 *>(A.mz + base + lo);
         const double2 *r2 = reinterpret_cast<const double2 *>(A.rho + base + lo);
-        for (size_t k = threadIdx.x; k < npair; k += CR_THREADS) {
-            const double2 e = __ldg(e2 + k), mx = __ldg(x2 + k), my = __ldg(y2 + k), mz = __ldg(z2 + k), rho = __ldg(r2 + k);
+        // the loads of the next pair are issued before the arithmetic of this one (twelve warps per SM do not
+        // hide an HBM round trip by themselves)
+        size_t k = threadIdx.x;
+        double2 e = make_double2(0, 0), mx = e, my = e, mz = e, rho = e;
+        if (k < npair) { e = __ldg(e2 + k); mx = __ldg(x2 + k); my = __ldg(y2 + k); mz = __ldg(z2 + k); rho = __ldg(r2 + k); }
+        while (k < npair) {
+            const size_t kn = k + CR_THREADS;
+            double2 en = e, mxn = mx, myn = my, mzn = mz, rhon = rho;
+            if (kn < npair) { en = __ldg(e2 + kn); mxn = __ldg(x2 + kn); myn = __ldg(y2 + kn); mzn = __ldg(z2 + kn); rhon = __ldg(r2 + kn); }
             accumulate_point(acc, A.beta, A.gamma, A.Ma, e.x, mx.x, my.x, mz.x, rho.x, viscous);
             accumulate_point(acc, A.beta, A.gamma, A.Ma, e.y, mx.y, my.y, mz.y, rho.y, viscous);
+            e = en; mx = mxn; my = myn; mz = mzn; rho = rhon; k = kn;
         }
         if (threadIdx.x == 0 && ((hi - lo) & 1)) {
             const size_t k = base + hi - 1;
@@ -156,7 +164,7 @@ int szb_collect_references_device(const szb_rholut_imexop_scenario *scenario, do
     SZB_CUDA_OK(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // blocks per plane: about two waves of three resident blocks per SM over all planes, at least 1 024 points per block
-    int nbx = ny > 0 ? (6 * sms + ny - 1) / ny : 1;
+    int nbx = ny > 0 ? std::max(1, 6 * sms / ny) : 1;       // rounded down: ny * nbx blocks fill two waves, not two and a bit
     const size_t maxb = (nzx + 1023) / 1024;
     if ((size_t) nbx > maxb) nbx = (int) std::max<size_t>(1, maxb);
     const size_t need = sizeof(double) * (size_t) std::max(ny, 1) * nbx * NQ;
