@@ -211,6 +211,16 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void dmma1684(double (&c)[4], double a0, double a1, double b)
+{
+    asm("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(a0), "d"(a1), "d"(b));
+}
+__device__ __forceinline__ void dmma1688(double (&c)[4], const double (&a)[4], double b0, double b1)
+{
+    asm("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b0), "d"(b1));
+}
 __device__ __forceinline__ double neg_if(double v, unsigned signmask)
 {
     return __hiloint2double(__double2hiint(v) ^ (int) signmask, __double2loint(v));
@@ -690,15 +700,15 @@ invert_sync_kernel(const PipeArgs A)
             }
             ju = max(ju, juc);
 #ifdef SZB_SYNC_U_DMMA
-            // (experiment, make XDEFS=-DSZB_SYNC_U_DMMA: correct, 20.3 ms against 19.4 ms -- the 8-byte fragment loads cost more
-            // shared-memory wavefronts than the scalar update's broadcast loads; see tools/experiments/README.md)
+            // (experiment, make XDEFS=-DSZB_SYNC_U_DMMA; see tools/experiments/README.md)
             // ---------------- P3: U(t) on the FP64 tensor cores.  The rank-5 complex update of the trailing block
             // (rows at positions 5..RW and the right-hand side, columns j+5..ju) is the real product
-            //   [C^T re | C^T im] += [U^T re | U^T im] (8 columns x 10, padded to 12) . B (12 x 8 = 4 rows x {re, im})
-            // with B = [-L re, -L im ; +L im, -L re]: one DMMA.8x8x4 chain of three per tile of 8 columns x 4 rows,
-            // a lane owning exactly one complex window element (column 8 mt + lane / 4, row 4 nt + lane % 4).  The
-            // tiles are dealt to the warps in contiguous runs of the (column tile, row tile) order, so the U^T
-            // fragments are loaded once per run.  Same FMAs as the scalar update, an eighth of the instructions.
+            //   [C^T re | C^T im] += A (16 columns x 12) . B (12 x 8 = 4 rows x {re, im})
+            // K ordered so that a lane's fragment entries are the two halves of ONE complex number:
+            //   k = q, q + 4 (q = lane % 4 < 4): re, im of U(q, column);  k = 8, 9: re, im of U(4, column);  10, 11: zero
+            //   B(k, 2 r + part): part 0 (real row):  -re L(r, q), +im L(r, q);  part 1 (imaginary row):  -im L, -re L
+            // one m16n8k8 + one m16n8k4 per tile of 16 columns x 4 rows = six DMMA.8x8x4 in two independent chains, a
+            // lane owning two complex window elements (columns 16 mt + lane / 4 and + 8, row 4 nt + lane % 4).
             {
                 constexpr int NNT = (W::NR + 3) / 4;                        // row tiles
                 constexpr unsigned ROWB = CW * sizeof(cplx);
@@ -706,44 +716,48 @@ invert_sync_kernel(const PipeArgs A)
                 const unsigned char *const prow = reinterpret_cast<const unsigned char *>(S.win + (size_t) jr * CW);
                 const unsigned char *const zerop = reinterpret_cast<const unsigned char *>(S.tbm + P);   // a 0.0
                 const unsigned char *const lpb = reinterpret_cast<const unsigned char *>(S.lp);
-                // K index kk = 4 s + lane % 4: U row kk % 5, real part for kk < 5, imaginary for 5 <= kk < 10, zero beyond
-                const unsigned ao0 = qd * ROWB, ao1 = qd == 0 ? 4 * ROWB : (qd - 1) * ROWB + 8, ao2 = (qd + 3) * ROWB + 8;
-                const bool kz = qd >= 2;                                    // kk = 10, 11 in the third step
-                // B: column 2 r' + part of the tile is the real (part 0) or imaginary (part 1) part of window row r'
-                const unsigned bo0 = (gr * P + qd) * 16 + 8 * part;
-                const unsigned bo1 = qd == 0 ? (gr * P + 4) * 16 + 8 * part : (gr * P + qd - 1) * 16 + 8 * (1 - part);
-                const unsigned bo2 = (gr * P + qd + 3) * 16 + 8 * (1 - part);
-                const unsigned ng1 = (qd == 0 || part) ? 0x80000000u : 0u, ng2 = part ? 0x80000000u : 0u;
-                const int nmt = (ncols + 7) >> 3, ntl = nmt * NNT;
+                const bool kz = qd >= 2;                                    // k = 10, 11
+                const unsigned bo = (gr * P + qd) * 16;                     // L(r, q) within the row tile
+                const unsigned bo4 = (gr * P + 4) * 16 + 8 * (qd == 0 ? part : 1 - part);
+                const unsigned ng4 = (qd == 1 && part == 0) ? 0u : 0x80000000u;
+                const int nmt = (ncols + 15) >> 4, ntl = nmt * NNT;
                 int id = (warp * ntl) / NWC;
                 const int idh = ((warp + 1) * ntl) / NWC;
                 int mt = id / NNT, nt = id - mt * NNT;
                 while (id < idh) {
-                    const int i = 8 * mt + g;
-                    int c = jc + P + i; if (c >= CW) c -= CW;
-                    const bool cv = i < ncols;
-                    if (!cv) c = jc;
-                    const unsigned char *const colp = prow + 16 * c;
-                    const double a0 = *reinterpret_cast<const double *>(colp + ao0);
-                    const double a1 = *reinterpret_cast<const double *>(colp + ao1);
-                    const double a2 = *reinterpret_cast<const double *>(kz ? zerop : colp + ao2);
+                    const int i0 = 16 * mt + g, i1 = i0 + 8;
+                    int c0 = jc + P + i0; if (c0 >= CW) c0 -= CW;
+                    int c1 = jc + P + i1; if (c1 >= CW) c1 -= CW;
+                    const bool cv0 = i0 < ncols, cv1 = i1 < ncols;
+                    if (!cv0) c0 = jc;
+                    if (!cv1) c1 = jc;
+                    const unsigned char *const col0 = prow + 16 * c0, *const col1 = prow + 16 * c1;
+                    double fa[4], fa4[2];
+                    {
+                        const cplx u0 = *reinterpret_cast<const cplx *>(col0 + qd * ROWB);
+                        const cplx u1 = *reinterpret_cast<const cplx *>(col1 + qd * ROWB);
+                        fa[0] = u0.x; fa[1] = u1.x; fa[2] = u0.y; fa[3] = u1.y;
+                        fa4[0] = *reinterpret_cast<const double *>(kz ? zerop : col0 + 4 * ROWB + 8 * qd);
+                        fa4[1] = *reinterpret_cast<const double *>(kz ? zerop : col1 + 4 * ROWB + 8 * qd);
+                    }
                     const int nte = min(NNT, nt + (idh - id));
                     id += nte - nt;
-#pragma unroll 2
                     for (; nt < nte; ++nt) {
                         const int pos = P + 4 * nt + qd;
                         int slot = RW;
                         if (pos < RW) { slot = jr + pos; if (slot >= RW) slot -= RW; }
-                        cplx *const cp = S.win + (size_t) slot * CW + c;
+                        cplx *const cp0 = S.win + (size_t) slot * CW + c0, *const cp1 = S.win + (size_t) slot * CW + c1;
                         const unsigned char *const bb = lpb + (P + 4 * nt) * P * 16;
-                        const double b0 = neg_if(*reinterpret_cast<const double *>(bb + bo0), 0x80000000u);
-                        const double b1 = neg_if(*reinterpret_cast<const double *>(bb + bo1), ng1);
-                        const double b2 = neg_if(*reinterpret_cast<const double *>(kz ? zerop : bb + bo2), ng2);
-                        cplx w = *cp;
-                        dmma884(w.x, w.y, a0, b0);
-                        dmma884(w.x, w.y, a1, b1);
-                        dmma884(w.x, w.y, a2, b2);
-                        if (cv && pos <= RW) *cp = w;
+                        const cplx l = *reinterpret_cast<const cplx *>(bb + bo);
+                        const double l4 = *reinterpret_cast<const double *>(kz ? zerop : bb + bo4);
+                        const double b0 = part ? -l.y : -l.x, b1 = part ? -l.x : l.y, b4 = neg_if(l4, ng4);
+                        cplx w0 = *cp0, w1 = *cp1;
+                        double cc[4] = { w0.x, w0.y, w1.x, w1.y };
+                        dmma1688(cc, fa, b0, b1);
+                        dmma1684(cc, fa4[0], fa4[1], b4);
+                        const bool rv = pos <= RW;
+                        if (cv0 && rv) *cp0 = cplx(cc[0], cc[1]);
+                        if (cv1 && rv) *cp1 = cplx(cc[2], cc[3]);
                     }
                     nt = 0; ++mt;
                 }
