@@ -52,6 +52,9 @@
 #ifndef SZB_SYNC_NDEF
 #define SZB_SYNC_NDEF 0
 #endif
+#ifndef SZB_SYNC_TAILDEF
+#define SZB_SYNC_TAILDEF 1
+#endif
 
 // Optional phase timing (make PROF=1): per-phase clock64() deltas of thread 0 (panel warp 0) in
 // slots 0..6 and of the first thread of the first non-panel warp in slots 8..14, summed over all
@@ -105,6 +108,7 @@ struct SyncCfg {
     static constexpr int NDEF = SZB_SYNC_NDEF;      // trailing columns left to the assembly warps of the next P1 (0: none)
     static constexpr int NR = RW - P + 1;           // rows of the trailing update (incl. the right-hand side)
     static constexpr int NMAIN = NR < 32 ? NR : 32, NTAIL = NR - NMAIN;
+    static constexpr bool TAILDEF = SZB_SYNC_TAILDEF != 0 && NTAIL > 0 && NTAIL <= 4;   // tail rows of U(t) applied in the next P1
     static constexpr int CH = 4, NB = 2;            // solver: L columns per TMA chunk, ring depth
     static_assert(KL_ == P * (KB + 1) - 1, "KL = 5 (kb + 1) - 1");
     static_assert(RW % P == 0 && CW % P == 0, "rows and column slots come in groups of five");
@@ -364,7 +368,7 @@ __device__ __forceinline__ void urows_column(const SM &S, int jr, int cs, cplx *
 // its use, four complex updates ahead of the next one (the compiler's own schedule went column by column, a chain
 // of ten dependent FMAs behind each load).
 // ---------------------------------------------------------------------------------------------
-template <class W, int NCHX, class SM>
+template <class W, int NCHX, bool TAILS, class SM>
 __device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, int istep, int ilim, int lane)
 {
     constexpr int RW = W::RW, CW = W::CW;
@@ -407,6 +411,7 @@ __device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, i
             for (int x = 0; x < NCHX; ++x) sts_if(ca[x] + dro, w[x], cv[x]);
         }
         // tail rows (positions 5 + NMAIN .. RW): one element per lane
+        if (TAILS)
         for (int e = lane; e < W::NTAIL * NCHX; e += 32) {
             const int x = e / (W::NTAIL > 0 ? W::NTAIL : 1), r = e - x * W::NTAIL;
             const int i = i0 + istep * (m0 + x);
@@ -424,6 +429,33 @@ __device__ __forceinline__ void u_columns(const SM &S, int jr, int jc, int i0, i
             for (int k = 0; k < P; ++k) submul(w, ll[k], uu[k]);
             sts_if(pw, w, i < ilim);
         }
+    }
+}
+
+// The tail rows of U(t) (positions 5 + NMAIN .. RW, the right-hand side among them) for all trailing columns, one
+// element per thread of a group of nt threads: they are 4 of 36 rows but a quarter of the time of a lane = row pass
+// (a serial chain per element), and nothing needs them before F2(t+1), so the assembly warps apply them in the
+// next phase 1 while F1(t+1) runs (W::TAILDEF).
+template <class W, class SM>
+__device__ __forceinline__ void u_tails(const SM &S, int jr, int jc, int ncols, int t0, int nt)
+{
+    constexpr int RW = W::RW, CW = W::CW;
+    constexpr unsigned ROWB = CW * sizeof(cplx);
+    const unsigned prow_sa = smem_u32(S.win + (size_t) jr * CW);
+    for (int e = t0; e < W::NTAIL * ncols; e += nt) {
+        const int i = e / (W::NTAIL > 0 ? W::NTAIL : 1), r = e - i * W::NTAIL;
+        int c = jc + P + i; if (c >= CW) c -= CW;
+        const int tp = P + W::NMAIN + r;
+        int ts = RW;
+        if (tp < RW) { ts = jr + tp; if (ts >= RW) ts -= RW; }
+        const unsigned pu = prow_sa + 16u * (unsigned) c, pw = smem_u32(S.win + (size_t) ts * CW + c);
+        const unsigned pl = smem_u32(S.lp + tp * P);
+        cplx w = lds_c(pw), uu[P], ll[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) { uu[k] = lds_c(pu + k * ROWB); ll[k] = lds_c(pl + 16 * k); }
+#pragma unroll
+        for (int k = 0; k < P; ++k) submul(w, ll[k], uu[k]);
+        sts_if(pw, w, true);
     }
 }
 
@@ -606,13 +638,14 @@ invert_sync_kernel(const PipeArgs A)
                 const int yI = (j - P + RW) / P;
                 int jro = jr - P; if (jro < 0) jro += RW;
                 int jco = jc - P; if (jco < 0) jco += CW;
-                if (W::NDEF > 0) {
-                    // the last columns of U(t-1), then (all of them done) the retired pivot rows may be overwritten
+                if (W::NDEF > 0 || W::TAILDEF) {
+                    // what is left of U(t-1): its tail rows and / or its last columns; then (all of it done) the
+                    // retired pivot rows may be overwritten
                     const int ncp = min(ju, N - 1) - j + 1;
-                    if (ncp >= W::NDEF + 2 * P) {
-                        u_columns<W, 1>(S, jro, jco, ncp - W::NDEF + warp - 1, NWC - 1, ncp, lane);
-                        bar_sync_n<BAR_ASM>(NTA);
-                    }
+                    if (W::NDEF > 0 && ncp >= W::NDEF + 2 * P)
+                        u_columns<W, 1, !W::TAILDEF>(S, jro, jco, ncp - W::NDEF + warp - 1, NWC - 1, ncp, lane);
+                    if (W::TAILDEF && ncp > 0) u_tails<W>(S, jro, jco, ncp, ta, NTA);
+                    if (ncp > 0) bar_sync_n<BAR_ASM>(NTA);
                 }
                 cplx *dst = S.win + (size_t) jro * CW;
                 if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
@@ -767,7 +800,7 @@ invert_sync_kernel(const PipeArgs A)
             // ND columns are left to the assembly warps of the next P1, which would otherwise wait for F1(t+1). ----------------
             {
                 const int nd = ncols >= W::NDEF + 2 * P ? W::NDEF : 0;
-                u_columns<W, NCH>(S, jr, jc, warp, NWC, ncols - nd, lane);
+                u_columns<W, NCH, !W::TAILDEF>(S, jr, jc, warp, NWC, ncols - nd, lane);
             }
 #endif
             SPROF_MARK(4);
