@@ -1,6 +1,9 @@
 // capi.cu -- HOST-pointer entry points of the C ABI: per-pencil wrappers with the
 // reference's signatures, the three whole-field virtuals of
 // operator_hybrid_isothermal, and the batched B-spline operator apply.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -214,18 +217,17 @@ int build_ctx(const szb_wavegrid *g, FieldCtx &F)
     for (int r = 0; r < F.nz; ++r) nrows_active += row_active[r];
     auto cut = [&](std::vector<int> sizes, std::vector<Chunk> &out) {
         size_t si = 0;
+        int left = sizes.empty() ? nrows_active : std::max(sizes[0], 1);
         for (int r = 0; r < F.nz;) {
             if (!row_active[r]) { ++r; continue; }
-            const int per = si < sizes.size() ? std::max(sizes[si], 1) : nrows_active;
             int e = r;
-            while (e < F.nz && row_active[e] && e - r < per) ++e;
-            // an inactive row inside the range ends the chunk early: carry the rest over
-            if (si < sizes.size()) {
-                const int done = e - r;
-                if (done < per && si + 1 < sizes.size()) sizes[si + 1] += per - done;
-                ++si;
-            }
+            while (e < F.nz && row_active[e] && e - r < left) ++e;
+            // an inactive row inside the range (the dealiased gap between the positive and the negative kz) ends
+            // the chunk early; what is left of its size becomes a chunk of its own, so that the planned LAST chunk
+            // stays as short as planned (its download is the exposed one)
             out.push_back(Chunk{ r, e - r, row_a0[r], row_a0[e] });
+            left -= e - r;
+            if (left <= 0) { ++si; left = si < sizes.size() ? std::max(sizes[si], 1) : nrows_active; }
             r = e;
         }
     };
@@ -389,6 +391,10 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
     if (nconstraints < 0) return -6;
     if (nconstraints > 0 && !ic0) return -7;
     if (first_bad_pencil) *first_bad_pencil = -1;
+    static const bool trace = std::getenv("SZB_HOST_TRACE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(); };
+    double tr[6] = {0, 0, 0, 0, 0, 0};
     FieldCtx *F;
     int rc = get_ctx(op, g, &F);
     if (rc) return rc;
@@ -417,19 +423,67 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
         SZB_CUDA_OK(cudaMemcpyAsync(ic0, dic.p, sizeof(szb_complex) * N * nconstraints,
                                     cudaMemcpyDeviceToHost, F->s_comp));
     }
-    for (size_t c = 0; c < F->chunks_inv.size(); ++c) {
+    // zcgbsvx / zgbsvx around the fused kernel: the refinement passes run over the few pencils that go on and are
+    // latency-bound, so one refinement per chunk would cost as much as one over the whole field, three times.  All
+    // chunks but the last get their first solve as they arrive and ONE refinement together (their downloads then
+    // overlap the last chunk's solve); the last chunk is solved and refined on its own.
+    const size_t nch = F->chunks_inv.size();
+    std::vector<cudaEvent_t> tev;                              // SZB_HOST_TRACE: device-side timeline
+    std::vector<const char *> tname;
+    auto mark = [&](const char *name, cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); tname.push_back(name);
+    };
+    mark("start", F->s_in);
+    const bool refined_zc = spec->method == SZB_SOLVER_ZCGBSVX && spec->tolsc == 0.0 && spec->aiter >= 1;
+    const bool refined_zx = spec->method == SZB_SOLVER_ZGBSVX && !spec->equil;
+    static const bool staging = [] { const char *e = std::getenv("SZB_HOST_STAGED"); return !(e && e[0] == '0'); }();
+    bool staged = staging && nch >= 3 && (refined_zc || refined_zx) && op->linearization == SZB_LINEARIZE_RHOME_XYZ;
+    const int g0 = F->chunks_inv[0].a0, g1 = nch >= 2 ? F->chunks_inv[nch - 2].a1 : 0;    // union of all chunks but the last
+    for (size_t c = 0; c < nch; ++c) {
         const Chunk &ch = F->chunks_inv[c];
         if ((rc = copy_interleaved(*F, ch, N, F->d_a.p, state, cudaMemcpyHostToDevice, F->s_in))) return rc;
+        mark("upload", F->s_in);
         SZB_CUDA_OK(cudaEventRecord(F->ev_in[c], F->s_in));
         SZB_CUDA_OK(cudaStreamWaitEvent(F->s_comp, F->ev_in[c], 0));
+        if (staged && c + 1 < nch) {
+            rc = szb::invert_refined_stage(op, refined_zx ? 1 : 0, spec->aiter, spec->diter, phi, ch.a1 - ch.a0,
+                                           F->d_km.p + ch.a0, F->d_kn.p + ch.a0, F->d_act.p + ch.a0,
+                                           reinterpret_cast<szb::cplx *>(F->d_a.p), op->n, N, nullptr, F->d_info.p + ch.a0,
+                                           nullptr, F->s_comp, 1, ch.a0 - g0, g1 - g0);
+            if (rc == 1 && c == 0) staged = false;               // no fused kernel for this operator: plain path below
+            else if (rc) return rc;
+            if (staged) {
+                mark("first solve", F->s_comp);
+                if (c + 2 < nch) continue;
+                // the last of the group: refine the union, then release every download of the group
+                rc = szb::invert_refined_stage(op, refined_zx ? 1 : 0, spec->aiter, spec->diter, phi, g1 - g0,
+                                               F->d_km.p + g0, F->d_kn.p + g0, F->d_act.p + g0,
+                                               reinterpret_cast<szb::cplx *>(F->d_a.p), op->n, N, nullptr, F->d_info.p + g0,
+                                               nullptr, F->s_comp, 2, 0, g1 - g0);
+                if (rc) return rc;
+                mark("refinement", F->s_comp);
+                SZB_CUDA_OK(cudaEventRecord(F->ev_done[c], F->s_comp));
+                SZB_CUDA_OK(cudaStreamWaitEvent(F->s_out, F->ev_done[c], 0));
+                for (size_t d = 0; d <= c; ++d) {
+                    if ((rc = copy_interleaved(*F, F->chunks_inv[d], N, state, F->d_a.p, cudaMemcpyDeviceToHost, F->s_out)))
+                        return rc;
+                    mark("download", F->s_out);
+                }
+                continue;
+            }
+        }
         rc = szb_imexop_invert_batch(op, spec, phi, ch.a1 - ch.a0, F->d_km.p + ch.a0, F->d_kn.p + ch.a0,
                                      F->d_act.p + ch.a0, F->d_a.p, op->n, N, 0, nullptr, nullptr,
                                      F->d_info.p + ch.a0, nullptr, F->s_comp);
         if (rc) return rc;
+        mark("solve", F->s_comp);
         SZB_CUDA_OK(cudaEventRecord(F->ev_done[c], F->s_comp));
         SZB_CUDA_OK(cudaStreamWaitEvent(F->s_out, F->ev_done[c], 0));
         if ((rc = copy_interleaved(*F, ch, N, state, F->d_a.p, cudaMemcpyDeviceToHost, F->s_out))) return rc;
+        mark("download", F->s_out);
     }
+    tr[0] = since();
     // dealiased / Nyquist pencils are zero-filled (:632-637): on the host, they never travel
     // (a few host threads: 180 MB on the bench grid, done while the device works on the active pencils)
     {
@@ -447,10 +501,25 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
             for (auto &th : pool) th.join();
         }
     }
+    tr[1] = since();
     SZB_CUDA_OK(cudaStreamSynchronize(F->s_comp));
+    tr[2] = since();
     SZB_CUDA_OK(cudaMemcpy(info.data(), F->d_info.p, sizeof(int) * (F->nact + (nconstraints > 0)),
                            cudaMemcpyDeviceToHost));
+    tr[3] = since();
     SZB_CUDA_OK(cudaStreamSynchronize(F->s_out));
+    tr[4] = since();
+    if (trace) {
+        for (size_t i = 1; i < tev.size(); ++i) {
+            float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]);
+            std::fprintf(stderr, "  %s @ %.2f", tname[i], ms);
+        }
+        std::fprintf(stderr, "\n");
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    if (trace)
+        std::fprintf(stderr, "invert host: enqueued %.2f, zero-fill done %.2f, compute done %.2f, info %.2f, downloads done %.2f ms\n",
+                     tr[0], tr[1], tr[2], tr[3], tr[4]);
     for (int p = 0; p < F->nact + (nconstraints > 0); ++p) {
         if (info[p]) {
             if (first_bad_pencil) *first_bad_pencil = p < F->nact ? F->active_idx[p] : F->active_idx[F->zero_zero];

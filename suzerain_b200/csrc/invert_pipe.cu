@@ -1095,14 +1095,31 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                             int *d_iters, cudaStream_t stream)
 {
+    return invert_refined_stage(op, mode, aiter, dmax, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info,
+                                d_iters, stream, 3, 0, npencil);
+}
+
+// The same in two stages, for a caller that feeds the pencils in pieces (the whole-field host entry point uploads
+// wave space chunk by chunk): stage 1 = right-hand sides saved + first solve of `npencil` pencils that occupy
+// positions pos0 .. pos0 + npencil - 1 of a list of `capacity` pencils; stage 2 = the refinement loop over positions
+// 0 .. npencil - 1 (pos0 = 0), whose first solves have all been issued.  The pointer arguments always describe the
+// pencils of THIS call.  One refinement over the union of several chunks costs what one over a single chunk does
+// (its passes over the few pencils that go on are latency-bound).
+int invert_refined_stage(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
+                         const double *d_km, const double *d_kn, const int *d_index,
+                         cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                         int *d_iters, cudaStream_t stream, int stages, int pos0, int capacity)
+{
     // applicability first: nothing may have been launched when the caller is told to fall back
     if (op->A.KL != op->A.KU || dmax < 0) return 1;
+    if (!(op->A.KL == 14 || op->A.KL == 24 || op->A.KL == 34 || op->A.KL == 44)) return 1;   // the fused kernels' orders
     if (!mode && aiter < 1) return 1;       // lastres starts at 3: exact for aiter >= 1 (dsgbsvx.def:271-284)
+    if (pos0 < 0 || pos0 + npencil > capacity || ((stages & 2) && pos0 != 0)) return -4;
     const int N = op->A.N, n = op->n;
     // workspace: b, r | res, lastres, kma, kna | diter, cont, pos, info2, count
-    const size_t nb = (size_t) npencil * N * sizeof(cplx);
-    const size_t nd = (((size_t) npencil * sizeof(double)) + 15) & ~(size_t) 15;
-    const size_t ni = (((size_t) npencil * sizeof(int)) + 15) & ~(size_t) 15;
+    const size_t nb = (size_t) capacity * N * sizeof(cplx);
+    const size_t nd = (((size_t) capacity * sizeof(double)) + 15) & ~(size_t) 15;
+    const size_t ni = (((size_t) capacity * sizeof(int)) + 15) & ~(size_t) 15;
     const size_t need = 2 * nb + 4 * nd + 5 * ni + 16;
     if (need > op->refine_bytes) {
         if (op->d_refine) SZB_CUDA_OK(cudaFree(op->d_refine));
@@ -1125,13 +1142,17 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
     int *count = reinterpret_cast<int *>(w);
 
     if (mode) { aiter = 1; dmax = 5; }                    // zgbrfs: ITMAX
-    refine_gather_kernel<<<npencil, 128, 0, stream>>>(npencil, N, n, d_index, d_state, fs, ps, B, lastres,
-                                                      mode ? 3.0 : 0.0);
-    count_launch();
-    // first pass: x = 0 + (LU)^-T b, in place in the state
-    int rc = invert_fused_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info,
+    int rc = 0;
+    if (stages & 1) {
+        refine_gather_kernel<<<npencil, 128, 0, stream>>>(npencil, N, n, d_index, d_state, fs, ps, B + (size_t) pos0 * N,
+                                                          lastres + pos0, mode ? 3.0 : 0.0);
+        count_launch();
+        // first pass: x = 0 + (LU)^-T b, in place in the state
+        rc = invert_fused_dispatch(op, phi, npencil, d_km, d_kn, d_index, d_state, fs, ps, d_ipiv, d_info,
                                    nullptr, stream, 1);
-    if (rc) return rc;
+        if (rc) return rc;
+    }
+    if (!(stages & 2)) { SZB_CUDA_OK(cudaGetLastError()); return 0; }
     ResidualArgs A;
     fill_pack_args(op, phi, d_km, d_kn, 0, 1, nullptr, A.pk);
     A.nlist = npencil; A.pos = nullptr; A.index = d_index;

@@ -47,6 +47,12 @@ int invert_refined_dispatch(const szb_imexop *op, int mode, int aiter, int dmax,
                             const double *d_km, const double *d_kn, const int *d_index,
                             cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
                             int *d_iters, cudaStream_t stream);
+// stage 1: save b + first solve of pencils at positions pos0.. of a list of `capacity`; stage 2: the refinement
+// loop over positions 0 .. npencil - 1 (stages = 1 | 2: both, as invert_refined_dispatch)
+int invert_refined_stage(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
+                         const double *d_km, const double *d_kn, const int *d_index,
+                         cplx *d_state, size_t fs, size_t ps, int *d_ipiv, int *d_info,
+                         int *d_iters, cudaStream_t stream, int stages, int pos0, int capacity);
 int invert00_dispatch(const szb_imexop *op, int mode, int aiter, int dmax, const double phi[2], int npencil,
                       const int *d_index, cplx *d_state, size_t fs, size_t ps, int nextra, cplx *d_extra,
                       int *d_ipiv, int *d_info, int *d_iters, cudaStream_t stream);
