@@ -287,12 +287,12 @@ __device__ __forceinline__ bool panel_top(const SM &S, cplx *Lcol, unsigned char
         bad |= !(pm > 1e-140 && pm < 1e140);
         sts_if(lp_sa + 16 * k, l, has);
         st_global_if(Lrow + k * (KL - 1), l, below);                  // L(j+s, j+k) at Lcol[k (KL - 1) + s], zgbtf2 order
-        const bool piv = s == k;
-        sts_if(tr_sa + 16 * k, rs, piv);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}"
-                     :: "r"(tm_sa + 8 * k), "d"(mag), "r"((int) piv) : "memory");
+        // the published pivot row: every lane holds the same shuffled values, so every lane stores them (one
+        // wavefront, no predicate -- ptxas turns a run of equally predicated stores into a divergent branch region)
+        sts_if(tr_sa + 16 * k, rinv, true);
+        asm volatile("st.shared.f64 [%0], %1;" :: "r"(tm_sa + 8 * k), "d"(pm) : "memory");
 #pragma unroll
-        for (int m = k + 1; m < P; ++m) sts_if(tb_sa + 16 * (k * (9 - k) / 2 + m - k - 1), pv[m], piv);
+        for (int m = k + 1; m < P; ++m) sts_if(tb_sa + 16 * (k * (9 - k) / 2 + m - k - 1), pv[m], true);
     }
     if (has) jpv[j + s] = 0;
     return __any_sync(0xffffffffu, bad);
