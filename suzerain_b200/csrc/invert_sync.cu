@@ -634,6 +634,13 @@ invert_sync_kernel(const PipeArgs A)
                         }
                     }
                 }
+                // ... and the five right-hand-side entries that refill the recycled column slots (the only global load
+                // of the assembly; five threads of one warp, which the whole warp would wait for)
+                cplx rhsv(0.0, 0.0);
+                if (j > 0 && ta >= (RW - P) * P && ta < (RW - P) * P + P) {
+                    const int cn = j - P + CW + (ta - (RW - P) * P);
+                    if (cn < N) rhsv = ldcg_c(sv + cn);
+                }
               if (j > 0) {
                 const int yI = (j - P + RW) / P;
                 int jro = jr - P; if (jro < 0) jro += RW;
@@ -657,7 +664,10 @@ invert_sync_kernel(const PipeArgs A)
                     int slot = RW;
                     if (sp < RW - P) { slot = jr + sp; if (slot >= RW) slot -= RW; }
                     cplx val(0.0, 0.0);
-                    if (sp == RW - P) { const int cn = j - P + CW + m; if (cn < N) val = ldcg_c(sv + cn); }
+                    if (sp == RW - P) {
+                        if (e == ta) val = rhsv;
+                        else { const int cn = j - P + CW + m; if (cn < N) val = ldcg_c(sv + cn); }
+                    }
                     S.win[(size_t) slot * CW + jco + m] = val;
                 }
               }
