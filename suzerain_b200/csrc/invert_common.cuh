@@ -226,5 +226,44 @@ __device__ __forceinline__ void assemble_block_interior(const PackArgs &A, const
     }
 }
 
+// The same in two steps, for a caller that has to wait for other warps before it may overwrite dst (the rows
+// being replaced are still read by them): compute() forms this thread's entries in registers, store() writes them.
+template <class W, int NTHR>
+struct InteriorBlock {
+    static constexpr int NE = (P * W::CW + NTHR - 1) / NTHR;      // entries per thread
+    cplx v[NE];
+    int off[NE];                                                  // offset in dst, -1: none
+    template <class SM>
+    __device__ __forceinline__ void compute(const PackArgs &A, const SM &S, const double *rowblk, int yI, int t0)
+    {
+#pragma unroll
+        for (int q = 0; q < NE; ++q) {
+            const int e = t0 + q * NTHR;
+            v[q] = cplx(0.0, 0.0); off[q] = -1;
+            if (e < P * W::CW) {
+                const int sI = e / W::CW, ci = e - sI * W::CW;
+                const int J = 5 * yI + sI - W::KL + ci;                 // > 0 here
+                const int yJ = J / 5, sJ = J - 5 * yJ;
+                const int r = A.ku + yI - yJ;
+                if (ci <= W::KV && r >= 0 && r < A.ld) {
+                    const double m0 = rowblk[r], d1 = rowblk[A.ld + r], d2 = rowblk[2 * A.ld + r];
+                    cplx buf = S.coef[coef_index<W>(yJ, sJ, sI, 0)] * m0;
+                    buf += S.coef[coef_index<W>(yJ, sJ, sI, 1)] * d1;
+                    buf += S.coef[coef_index<W>(yJ, sJ, sI, 2)] * d2;
+                    buf = A.phi * buf;
+                    if (sI == sJ) buf += cplx(m0, 0.0);
+                    v[q] = buf;
+                }
+                off[q] = sI * W::CW + J % W::CW;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(cplx *dst) const
+    {
+#pragma unroll
+        for (int q = 0; q < NE; ++q) if (off[q] >= 0) dst[off[q]] = v[q];
+    }
+};
+
 }  // namespace fused
 }  // namespace szb

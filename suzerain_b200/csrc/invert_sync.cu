@@ -59,8 +59,14 @@
 // Optional phase timing (make PROF=1): per-phase clock64() deltas of thread 0 (panel warp 0) in
 // slots 0..6 and of the first thread of the first non-panel warp in slots 8..14, summed over all
 // pencils and CTAs; slot 7 counts exact-path panels, slot 15 all panels.  szb_debug_sync_prof().
+#ifndef SZB_SPROF_T1
+#define SZB_SPROF_T1 64
+#endif
+#ifndef SZB_SPROF_T2
+#define SZB_SPROF_T2 160
+#endif
 #ifdef SZB_PIPE_PROF
-// work / wait clocks of three threads (first lanes of warps 0, 2, 5), 8 slots each:
+// work / wait clocks of three threads (first lanes of warps 0, 2, 5; -DSZB_SPROF_T1= / T2= pick others), 8 slots each:
 // [P1 work, B1 wait, P2 work, B2 wait, P3 work, B3 wait, exact-path panels, panels]
 __device__ unsigned long long g_sync_prof[24];
 // the clock is read only once a shared-memory load issued after the barrier has returned:
@@ -645,20 +651,25 @@ invert_sync_kernel(const PipeArgs A)
                 const int yI = (j - P + RW) / P;
                 int jro = jr - P; if (jro < 0) jro += RW;
                 int jco = jc - P; if (jco < 0) jco += CW;
-                if (W::NDEF > 0 || W::TAILDEF) {
-                    // what is left of U(t-1): its tail rows and / or its last columns; then (all of it done) the
-                    // retired pivot rows may be overwritten
-                    const int ncp = min(ju, N - 1) - j + 1;
-                    if (W::NDEF > 0 && ncp >= W::NDEF + 2 * P)
-                        u_columns<W, 1, !W::TAILDEF>(S, jro, jco, ncp - W::NDEF + warp - 1, NWC - 1, ncp, lane);
-                    if (W::TAILDEF && ncp > 0) u_tails<W>(S, jro, jco, ncp, ta, NTA);
-                    if (ncp > 0) bar_sync_n<BAR_ASM>(NTA);
-                }
                 cplx *dst = S.win + (size_t) jro * CW;
-                if (yI - K.kl >= 1 && yI + K.ku <= n - 2)
-                    assemble_block_interior<W>(K, S, S.drow, yI, dst, ta, NTA);
-                else
+                const bool interior = yI - K.kl >= 1 && yI + K.ku <= n - 2;
+                const int ncp = (W::NDEF > 0 || W::TAILDEF) ? min(ju, N - 1) - j + 1 : 0;
+                // what is left of U(t-1): its tail rows and / or its last columns; only when all of it is done may the
+                // retired pivot rows be overwritten (a barrier of the assembly warps).  The entries of an interior block
+                // row are formed BEFORE that barrier, in registers, and stored after it: the warps without tail elements
+                // do not idle, and nobody waits twice.
+                if (W::NDEF > 0 && ncp >= W::NDEF + 2 * P)
+                    u_columns<W, 1, !W::TAILDEF>(S, jro, jco, ncp - W::NDEF + warp - 1, NWC - 1, ncp, lane);
+                if (W::TAILDEF && ncp > 0) u_tails<W>(S, jro, jco, ncp, ta, NTA);
+                if (interior) {
+                    InteriorBlock<W, NTA> blk;
+                    blk.compute(K, S, S.drow, yI, ta);
+                    if (ncp > 0) bar_sync_n<BAR_ASM>(NTA);
+                    blk.store(dst);
+                } else {
+                    if (ncp > 0) bar_sync_n<BAR_ASM>(NTA);
                     assemble_block<W>(K, S, K.km[p], K.kn[p], yI, dst, ta, NTA);
+                }
                 for (int e = ta; e < (NS - P) * P; e += NTA) {
                     const int sp = e / P, m = e - sp * P;                      // rows at positions 0..NS-P-1 of THIS panel
                     int slot = RW;
@@ -821,8 +832,8 @@ invert_sync_kernel(const PipeArgs A)
         }
 #ifdef SZB_PIPE_PROF
         if (tid == 0) SPROF_FLUSH(0);
-        if (tid == 64) SPROF_FLUSH(8);
-        if (tid == 160) SPROF_FLUSH(16);
+        if (tid == SZB_SPROF_T1) SPROF_FLUSH(8);
+        if (tid == SZB_SPROF_T2) SPROF_FLUSH(16);
 #endif
         if (tid == 0) { S.misc[buf] = info; if (info) for (int k = 0; k < N; ++k) jpv[k] = 0; }
         __threadfence();
