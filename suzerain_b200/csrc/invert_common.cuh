@@ -168,10 +168,25 @@ __device__ __forceinline__ void compute_coef_staged(const PackArgs &A, const SM 
                                                     const double *refcol, int t0, int nt)
 {
     if (y < 0 || y >= A.n) return;
+    // the loads of four terms are issued together (a block has at most seven): the plain loop is a chain of
+    // three dependent shared-memory loads per term.  Same summation order.
     for (int idx = t0; idx < W::NCOEF; idx += nt) {
         const int tb = S.tblk[idx], te = S.tblk[idx + 1];
         cplx c(0.0, 0.0);
-        for (int t = tb; t < te; ++t) c += S.alpha[t] * refcol[S.tref[t]];
+        for (int tq = tb; tq < te; tq += 4) {
+            cplx al[4]; double rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool ok = tq + u < te;
+                const int t = ok ? tq + u : tb;
+                const double r = refcol[S.tref[t]];
+                const cplx a = S.alpha[t];
+                rr[u] = ok ? r : 0.0;
+                al[u] = ok ? a : cplx(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c += al[u] * rr[u];
+        }
         S.coef[coef_index<W>(y, idx / 15, (idx / 3) % 5, idx % 3)] = c;
     }
 }
