@@ -439,7 +439,7 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
     const bool refined_zx = spec->method == SZB_SOLVER_ZGBSVX && !spec->equil;
     static const bool staging = [] { const char *e = std::getenv("SZB_HOST_STAGED"); return !(e && e[0] == '0'); }();
     bool staged = staging && nch >= 3 && (refined_zc || refined_zx) && op->linearization == SZB_LINEARIZE_RHOME_XYZ;
-    const int g0 = F->chunks_inv[0].a0, g1 = nch >= 2 ? F->chunks_inv[nch - 2].a1 : 0;    // union of all chunks but the last
+    const int g0 = nch >= 1 ? F->chunks_inv[0].a0 : 0, g1 = nch >= 2 ? F->chunks_inv[nch - 2].a1 : 0;    // union of all chunks but the last
     for (size_t c = 0; c < nch; ++c) {
         const Chunk &ch = F->chunks_inv[c];
         if ((rc = copy_interleaved(*F, ch, N, F->d_a.p, state, cudaMemcpyHostToDevice, F->s_in))) return rc;

@@ -604,3 +604,34 @@ def test_collect_references_feeds_the_operator(dev):
         col = r[:, port.REFERENCE_QUANTITIES.index(name)]
         assert float(((col - mean).abs() / mean.abs()).max()) <= TOL
     assert bool(torch.isfinite(r).all())
+
+
+# ---------------------------------------------------------------------------
+# the whole-field HOST entry points on a rank's sub-grid (what bench.py's e2e leg calls under torchrun):
+# kz blocks that contain the dealiased gap, end in it, or consist of dealiased rows only
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("solver", ["zgbsv", "zcgbsvx"])
+def test_host_invert_on_kz_blocks_matches_whole_field(dev, solver):
+    import suzerain_b200 as sz
+    from suzerain_b200 import synth
+    case = pc.make_case("tiny_16x24x16")
+    g = sz.wavegrid(16, 16, synth.LX, synth.LZ)
+    km, kn, act = sz.wavenumbers(g)
+    state = synth.state(km, kn, 24, synth.SEED)
+    op = pc.make_imexop(case)
+    whole = state.copy()
+    sz.OperatorHybridIsothermal(op, g, sz.SolverSpec(method=solver)).invert_mass_plus_scaled_operator(case.phi, whole)
+    nx = g.dkex - g.dkbx
+    nz = g.dkez - g.dkbz
+    rows = np.flatnonzero(act.reshape(nz, nx).any(axis=1))
+    gap = [r for r in range(nz) if r not in rows]
+    assert gap, "the dealiased grid has inactive kz rows"
+    # blocks: [0, inside the gap), [inside the gap, gap end + 2), [a block of dealiased rows only], [rest]
+    cuts = [0, gap[1], gap[-1] + 3, nz]
+    blocks = [(cuts[i], cuts[i + 1]) for i in range(3)] + [(gap[0], gap[-1] + 1)]
+    for lo, hi in blocks:
+        sub = sz.wavegrid(16, 16, synth.LX, synth.LZ, zrange=(g.dkbz + lo, g.dkbz + hi))
+        part = state[lo * nx:hi * nx].copy()
+        H = sz.OperatorHybridIsothermal(pc.make_imexop(case), sub, sz.SolverSpec(method=solver))
+        H.invert_mass_plus_scaled_operator(case.phi, part)
+        assert np.array_equal(part, whole[lo * nx:hi * nx]), (lo, hi)
