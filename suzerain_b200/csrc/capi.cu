@@ -437,7 +437,9 @@ int szb_operator_invert_mass_plus_scaled_operator(const szb_imexop *op,
     mark("start", F->s_in);
     const bool refined_zc = spec->method == SZB_SOLVER_ZCGBSVX && spec->tolsc == 0.0 && spec->aiter >= 1;
     const bool refined_zx = spec->method == SZB_SOLVER_ZGBSVX && !spec->equil;
-    static const bool staging = [] { const char *e = std::getenv("SZB_HOST_STAGED"); return !(e && e[0] == '0'); }();
+    // (off by default, SZB_HOST_STAGED=1: on one GPU it is a wash, 24.78 vs 24.85 ms, and with several ranks sharing the host's
+    // PCIe / memory system the late burst of downloads is no longer hidden: 4 GPUs 304 vs 276 ms per substep)
+    static const bool staging = [] { const char *e = std::getenv("SZB_HOST_STAGED"); return e && e[0] == '1'; }();
     bool staged = staging && nch >= 3 && (refined_zc || refined_zx) && op->linearization == SZB_LINEARIZE_RHOME_XYZ;
     const int g0 = nch >= 1 ? F->chunks_inv[0].a0 : 0, g1 = nch >= 2 ? F->chunks_inv[nch - 2].a1 : 0;    // union of all chunks but the last
     for (size_t c = 0; c < nch; ++c) {
