@@ -282,10 +282,13 @@ def test_shard_bounds_balance_active_pencils():
 
 
 def test_window_lu_models_match_lapack():
-    """The executable models of the fused kernels' index algebra and pipeline schedules (tools/); the
-    pipelined one also race-checks the split block update that is planned for the v4 kernel."""
+    """The executable models of the fused kernels' index algebra and schedules (tools/): the pipelined one race-checks
+    v4's split block update; the synchronous one runs v5's three phases with their concurrent roles (speculative panel,
+    exact fallback, tail rows of the trailing update deferred to the next phase 1), checks that no role writes what
+    another role of the same phase touches, that the barrier between the deferred tail rows and the assembly is needed,
+    and that pivots and solutions are LAPACK's."""
     import importlib.util
-    for name in ("window_lu_model", "blocked_window_model", "pipelined_window_model"):
+    for name in ("window_lu_model", "blocked_window_model", "pipelined_window_model", "sync_window_model"):
         spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
